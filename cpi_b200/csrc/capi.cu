@@ -1,0 +1,235 @@
+// extern "C" boundary of libcpi_b200.so (declared in include/cpi_b200.h).  Plain pointers and sizes only.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "cpi_common.cuh"
+#include "cpi_kernels.h"
+
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(CPI_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+struct DevInfo { int sms = 0; int max_smem = 0; bool ok = false; };
+int device_info(DevInfo& d) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(CPI_ENODEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    static std::mutex mu;
+    static DevInfo cache[64];
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 64 && cache[dev].ok) { d = cache[dev]; return CPI_OK; }
+    int major = 0;
+    CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return fail(CPI_ENODEVICE, "device %d is sm_%d*, this library is built for sm_100a (B200) only", dev, major * 10);
+    CU(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    CU(cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    d.ok = true;
+    if (dev < 64) cache[dev] = d;
+    return CPI_OK;
+}
+
+// grow-only scratch buffers for the *_host entry points (per process; guarded by one mutex: host calls serialise)
+struct Scratch {
+    void* dev[8] = {nullptr}; size_t dev_sz[8] = {0};
+    void* pin[4] = {nullptr}; size_t pin_sz[4] = {0};
+    cudaStream_t stream = nullptr;
+    int device = -1;
+};
+std::mutex g_scratch_mu;
+Scratch g_scratch;
+
+int scratch_prepare() {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (g_scratch.device != dev) {
+        // buffers belong to the device they were allocated on; drop them if the caller switched device
+        for (int i = 0; i < 8; i++) { if (g_scratch.dev[i]) cudaFree(g_scratch.dev[i]); g_scratch.dev[i] = nullptr; g_scratch.dev_sz[i] = 0; }
+        if (g_scratch.stream) { cudaStreamDestroy(g_scratch.stream); g_scratch.stream = nullptr; }
+        g_scratch.device = dev;
+    }
+    if (!g_scratch.stream) CU(cudaStreamCreateWithFlags(&g_scratch.stream, cudaStreamNonBlocking));
+    return CPI_OK;
+}
+int dev_buf(int slot, size_t bytes, void** out) {
+    if (bytes == 0) bytes = 8;
+    if (g_scratch.dev_sz[slot] < bytes) {
+        if (g_scratch.dev[slot]) CU(cudaFree(g_scratch.dev[slot]));
+        g_scratch.dev[slot] = nullptr; g_scratch.dev_sz[slot] = 0;
+        cudaError_t e = cudaMalloc(&g_scratch.dev[slot], bytes);
+        if (e != cudaSuccess) return fail(CPI_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        g_scratch.dev_sz[slot] = bytes;
+    }
+    *out = g_scratch.dev[slot];
+    return CPI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cpi_last_error(void) { return g_err.c_str(); }
+const char* cpi_version(void) { return "cpi_b200 0.1 (sm_100a)"; }
+int cpi_record_doubles(int model) { return model == 1 ? CPI_REC_V1_DOUBLES : (model == 2 ? CPI_REC_V2_DOUBLES : CPI_EINVAL); }
+int64_t cpi_launch_count(void) { return g_launches.load(); }
+
+int cpi_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(CPI_ENODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+int cpi_preintegrate_batch(int model, int dtype, int64_t n_windows, const int64_t* sample_offsets, int64_t ns_uniform,
+                           const void* samples, const void* lin, const double* sigmas, int flags, void* out_records, void* stream) {
+    if (model != 1 && model != 2) return fail(CPI_EINVAL, "model must be 1 or 2 (got %d)", model);
+    if (dtype != 64) return fail(CPI_EINVAL, "dtype %d not supported by this build (fp64 only)", dtype);
+    if (n_windows < 0 || (!sample_offsets && ns_uniform < 0)) return fail(CPI_EINVAL, "negative count");
+    if (n_windows == 0) return CPI_OK;
+    if (!lin || !sigmas || !out_records) return fail(CPI_EINVAL, "null pointer argument");
+    if (!samples && (sample_offsets || ns_uniform > 0)) return fail(CPI_EINVAL, "samples is null");
+    if (model == 1 && (flags & CPI_FLAG_ANALYTIC_JACOBIANS)) flags &= ~CPI_FLAG_ANALYTIC_JACOBIANS;   // model 1 is always analytic
+    DevInfo d;
+    int rc = device_info(d);
+    if (rc) return rc;
+    cpi::PreintParams p;
+    p.n_windows = n_windows; p.offsets = sample_offsets; p.ns_uniform = ns_uniform;
+    p.samples = (const double*)samples; p.lin = (const double*)lin; p.out = (double*)out_records;
+    p.q_w = sigmas[0] * sigmas[0]; p.q_wb = sigmas[1] * sigmas[1]; p.q_a = sigmas[2] * sigmas[2]; p.q_ab = sigmas[3] * sigmas[3];
+    p.wpb = 0;
+    int launches = 0;
+    CU(cpi::preint_launch(model, flags, p, d.sms, d.max_smem, (cudaStream_t)stream, &launches));
+    g_launches += launches;
+    return CPI_OK;
+}
+
+int cpi_preintegrate_batch_host(int model, int dtype, int64_t n_windows, const int64_t* sample_offsets, int64_t ns_uniform,
+                                const void* samples, const void* lin, const double* sigmas, int flags, void* out_records) {
+    if (model != 1 && model != 2) return fail(CPI_EINVAL, "model must be 1 or 2 (got %d)", model);
+    if (dtype != 64) return fail(CPI_EINVAL, "dtype %d not supported by this build (fp64 only)", dtype);
+    if (n_windows < 0) return fail(CPI_EINVAL, "negative count");
+    if (n_windows == 0) return CPI_OK;
+    if (!lin || !sigmas || !out_records) return fail(CPI_EINVAL, "null pointer argument");
+    const int avg = (flags & CPI_FLAG_IMU_AVG) ? 1 : 0;
+    const int64_t entries = sample_offsets ? sample_offsets[n_windows] : n_windows * (ns_uniform + avg);
+    if (entries > 0 && !samples) return fail(CPI_EINVAL, "samples is null");
+    const int rd = cpi_record_doubles(model);
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    int rc = scratch_prepare();
+    if (rc) return rc;
+    cudaStream_t st = g_scratch.stream;
+    void *d_s, *d_l, *d_o, *d_off = nullptr;
+    if ((rc = dev_buf(0, (size_t)entries * CPI_SAMPLE_DOUBLES * 8, &d_s))) return rc;
+    if ((rc = dev_buf(1, (size_t)n_windows * CPI_LIN_DOUBLES * 8, &d_l))) return rc;
+    if ((rc = dev_buf(2, (size_t)n_windows * rd * 8, &d_o))) return rc;
+    if (sample_offsets) {
+        if ((rc = dev_buf(3, (size_t)(n_windows + 1) * 8, &d_off))) return rc;
+        CU(cudaMemcpyAsync(d_off, sample_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaMemcpyAsync(d_l, lin, (size_t)n_windows * CPI_LIN_DOUBLES * 8, cudaMemcpyHostToDevice, st));
+    if (entries > 0) CU(cudaMemcpyAsync(d_s, samples, (size_t)entries * CPI_SAMPLE_DOUBLES * 8, cudaMemcpyHostToDevice, st));
+    rc = cpi_preintegrate_batch(model, dtype, n_windows, (const int64_t*)d_off, ns_uniform, d_s, d_l, sigmas, flags, d_o, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_records, d_o, (size_t)n_windows * rd * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return CPI_OK;
+}
+
+int cpi_imu_factor_eval_batch(int model, int64_t n_factors, const double* states, const int64_t* idx_i, const int64_t* idx_j,
+                              const double* records, const double* lin, double* e, double* H1, double* H2, void* stream) {
+    if (model != 1 && model != 2) return fail(CPI_EINVAL, "model must be 1 or 2 (got %d)", model);
+    if (n_factors < 0) return fail(CPI_EINVAL, "negative count");
+    if (n_factors == 0) return CPI_OK;
+    if (!states || !records || !lin || !e) return fail(CPI_EINVAL, "null pointer argument");
+    if ((idx_i == nullptr) != (idx_j == nullptr)) return fail(CPI_EINVAL, "idx_i and idx_j must both be given or both be null");
+    DevInfo d;
+    int rc = device_info(d);
+    if (rc) return rc;
+    cpi::FactorParams p{n_factors, states, idx_i, idx_j, records, lin, e, H1, H2};
+    CU(cpi::factor_launch(model, p, (cudaStream_t)stream));
+    g_launches += 1;
+    return CPI_OK;
+}
+
+int cpi_imu_factor_eval_batch_host(int model, int64_t n_factors, int64_t n_states, const double* states, const int64_t* idx_i,
+                                   const int64_t* idx_j, const double* records, const double* lin, double* e, double* H1, double* H2) {
+    if (model != 1 && model != 2) return fail(CPI_EINVAL, "model must be 1 or 2 (got %d)", model);
+    if (n_factors < 0 || n_states < 0) return fail(CPI_EINVAL, "negative count");
+    if (n_factors == 0) return CPI_OK;
+    if (!states || !records || !lin || !e) return fail(CPI_EINVAL, "null pointer argument");
+    if (!idx_i && n_states < n_factors + 1) return fail(CPI_EINVAL, "chain indexing needs n_states >= n_factors + 1");
+    const int rd = cpi_record_doubles(model);
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    int rc = scratch_prepare();
+    if (rc) return rc;
+    cudaStream_t st = g_scratch.stream;
+    void *d_x, *d_r, *d_l, *d_e, *d_h1 = nullptr, *d_h2 = nullptr, *d_i = nullptr, *d_j = nullptr;
+    if ((rc = dev_buf(0, (size_t)n_states * CPI_STATE_DOUBLES * 8, &d_x))) return rc;
+    if ((rc = dev_buf(1, (size_t)n_factors * CPI_LIN_DOUBLES * 8, &d_l))) return rc;
+    if ((rc = dev_buf(2, (size_t)n_factors * rd * 8, &d_r))) return rc;
+    if ((rc = dev_buf(4, (size_t)n_factors * 15 * 8, &d_e))) return rc;
+    if (H1 && (rc = dev_buf(5, (size_t)n_factors * 225 * 8, &d_h1))) return rc;
+    if (H2 && (rc = dev_buf(6, (size_t)n_factors * 225 * 8, &d_h2))) return rc;
+    if (idx_i) {
+        if ((rc = dev_buf(3, (size_t)n_factors * 8, &d_i))) return rc;
+        if ((rc = dev_buf(7, (size_t)n_factors * 8, &d_j))) return rc;
+        CU(cudaMemcpyAsync(d_i, idx_i, (size_t)n_factors * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_j, idx_j, (size_t)n_factors * 8, cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaMemcpyAsync(d_x, states, (size_t)n_states * CPI_STATE_DOUBLES * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_l, lin, (size_t)n_factors * CPI_LIN_DOUBLES * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_r, records, (size_t)n_factors * rd * 8, cudaMemcpyHostToDevice, st));
+    rc = cpi_imu_factor_eval_batch(model, n_factors, (const double*)d_x, (const int64_t*)d_i, (const int64_t*)d_j, (const double*)d_r,
+                                   (const double*)d_l, (double*)d_e, (double*)d_h1, (double*)d_h2, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(e, d_e, (size_t)n_factors * 15 * 8, cudaMemcpyDeviceToHost, st));
+    if (H1) CU(cudaMemcpyAsync(H1, d_h1, (size_t)n_factors * 225 * 8, cudaMemcpyDeviceToHost, st));
+    if (H2) CU(cudaMemcpyAsync(H2, d_h2, (size_t)n_factors * 225 * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return CPI_OK;
+}
+
+int cpi_predict_state_batch(int model, int64_t n, const double* states_k, const double* records, const double* lin, double* states_k1, void* stream) {
+    if (model != 1 && model != 2) return fail(CPI_EINVAL, "model must be 1 or 2 (got %d)", model);
+    if (n < 0) return fail(CPI_EINVAL, "negative count");
+    if (n == 0) return CPI_OK;
+    if (!states_k || !records || !lin || !states_k1) return fail(CPI_EINVAL, "null pointer argument");
+    DevInfo d;
+    int rc = device_info(d);
+    if (rc) return rc;
+    CU(cpi::predict_launch(model, n, states_k, records, lin, states_k1, (cudaStream_t)stream));
+    g_launches += 1;
+    return CPI_OK;
+}
+
+int cpi_retract_batch(int64_t n, const double* states, const double* xi, double* states_out, void* stream) {
+    if (n < 0) return fail(CPI_EINVAL, "negative count");
+    if (n == 0) return CPI_OK;
+    if (!states || !xi || !states_out) return fail(CPI_EINVAL, "null pointer argument");
+    DevInfo d;
+    int rc = device_info(d);
+    if (rc) return rc;
+    CU(cpi::retract_launch(n, states, xi, states_out, (cudaStream_t)stream));
+    g_launches += 1;
+    return CPI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,37 @@
+// Kernel parameter blocks and host-side launchers shared by capi.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cpi {
+
+struct PreintParams {
+    int64_t n_windows;
+    const int64_t* offsets;   // device, may be null (uniform windows)
+    int64_t ns_uniform;
+    const double* samples;    // device
+    const double* lin;        // device
+    double* out;              // device
+    double q_w, q_wb, q_a, q_ab;   // sigma^2  (CpiBase.h:54-57)
+    int wpb;                  // windows per block == shared-memory window stride (chosen by preint_launch)
+};
+
+struct FactorParams {
+    int64_t n;
+    const double* states;
+    const int64_t* idx_i;
+    const int64_t* idx_j;
+    const double* records;
+    const double* lin;
+    double* e;
+    double* H1;
+    double* H2;
+};
+
+int preint_pick_wpb(int model, int64_t n_windows, int num_sms, int max_smem_bytes);
+cudaError_t preint_launch(int model, int flags, const PreintParams& p0, int num_sms, int max_smem_bytes, cudaStream_t st, int* launches);
+cudaError_t factor_launch(int model, const FactorParams& p, cudaStream_t st);
+cudaError_t predict_launch(int model, int64_t n, const double* states, const double* records, const double* lin, double* out, cudaStream_t st);
+cudaError_t retract_launch(int64_t n, const double* states, const double* xi, double* out, cudaStream_t st);
+
+}  // namespace cpi

@@ -1,0 +1,785 @@
+// K1 / K2: batched closed-form IMU preintegration, CpiV1::feed_IMU (cpi/CpiV1.h:62-361) and CpiV2::feed_IMU
+// (cpi/CpiV2.h:84-467) of rpng/cpi, re-designed for B200 (sm_100a).  See DESIGN.md for the derivation.
+//
+// Mapping: ONE LANE PER WINDOW, a warp advances 32 independent windows in lock-step.  Measured on B200
+// (profiles/microbench_r01.jsonl): DFMA peak 34.2 TFLOP/s and a single warp per SMSP already reaches 90 % of it at
+// ILP >= 4, whereas every cross-lane double costs as much as 4 DFMA (SHFL / LDS bandwidth is 16 doubles/clk/SM vs 64
+// DFMA/clk/SM).  So the window recurrence is kept free of cross-lane traffic; the per-window state that does not fit
+// the register file -- the 90 unique non-trivial entries of the 15x15 covariance and its two RK4 work copies -- lives
+// in shared memory in [entry][window] order (conflict-free: lane == window).
+//
+// Arithmetic: the reference integrates  Pdot = F P + P F^T + G Qc G^T  with RK4, F evaluated at R_old / R_mid / R_mid /
+// R_new.  The same four stages are replicated here, but on the 3x3 block structure of F (five non-zero blocks), with P
+// symmetric (15 unique blocks, two of them identically zero, two of them scalar multiples of I):
+//     rows theta:  (FP)_tJ = -W P_tJ - P_gJ          W = [w_hat x]
+//     rows v:      (FP)_vJ =  A P_tJ + B P_aJ (+ C P_cJ, model 2)     A = -R*^T [a_hat x],  B = -R*^T,  C = -R*^T [g_tau x]
+//     rows p:      (FP)_pJ =  P_vJ
+// Model 2's 21x21 system reduces to the same 15x15 tile plus three transient 3x3 blocks (clone rows c) per step: the
+// theta_klin rows/cols of P_big are identically zero and the clone rows are re-initialised from the theta rows every
+// step (B_k, CpiV2.h:436-443).  Its Jacobians are read out of the compounded transition Discrete_J_b; only 7 of its
+// 3x3 blocks are ever non-trivial in the 9 consumed columns, and Phi's RK4 has closed block forms (see phi_blocks()).
+#include "cpi_common.cuh"
+#include "cpi_kernels.h"
+
+namespace cpi {
+
+// ---- shared-memory tile layout (unique entries of P_meas; units: doubles per window) --------------------------------
+enum : int {
+    TT = 0,   // P_theta,theta  sym 6
+    TG = 6,   // P_theta,bg     9   (i = theta row, j = bg col)
+    VT = 15,  // P_v,theta      9
+    VG = 24,  // P_v,bg         9
+    VV = 33,  // P_v,v          sym 6
+    VA = 39,  // P_v,ba         9
+    PT = 48,  // P_p,theta      9
+    PG = 57,  // P_p,bg         9
+    PV = 66,  // P_p,v          9
+    PA = 75,  // P_p,ba         9
+    PP = 84,  // P_p,p          sym 6
+    NP = 90,  // P_bg,bg = pgg*I and P_ba,ba = paa*I are scalars in registers; P_theta,ba = P_bg,ba = 0 identically
+    // model 2 only, work copy only (transient clone rows, CpiV2.h state 15:18)
+    CT = 90,  // P_c,theta 9
+    CV = 99,  // P_c,v     9
+    CP = 108, // P_c,p     9
+    NCUR2 = 117,
+    // model 2 only: the non-trivial blocks of Discrete_J_b in the consumed columns (bg, ba, theta_klin)
+    D_TG = 0, D_VG = 9, D_PG = 18, D_VA = 27, D_PA = 36, D_VL = 45, D_PL = 54, ND = 63
+};
+
+__host__ __device__ constexpr int tile_doubles(int model) { return model == 1 ? (NP * 3) : (NP * 2 + NCUR2 + ND); }
+
+
+// ---- block loaders ----------------------------------------------------------------------------------------------------
+#define SM(buf, idx) (buf)[(idx) * S]
+
+CPI_DEV void ld9(const double* b, int S, int off, double* x) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) x[k] = SM(b, off + k);
+}
+CPI_DEV void ldsym(const double* b, int S, int off, double* x) {   // packed sym -> full row-major 3x3
+    const double a0 = SM(b, off), a1 = SM(b, off + 1), a2 = SM(b, off + 2), a3 = SM(b, off + 3), a4 = SM(b, off + 4), a5 = SM(b, off + 5);
+    x[0] = a0; x[1] = a1; x[2] = a2; x[3] = a1; x[4] = a3; x[5] = a4; x[6] = a2; x[7] = a4; x[8] = a5;
+}
+
+// RK4 bookkeeping for one entry.  Reference: P2 = P + k1*dt/2, P3 = P + k2*dt/2, P4 = P + k3*dt,
+// P += (dt/6)*(k1 + 2 k2 + 2 k3 + k4)   (CpiV1.h:312, 323, 344, 352).
+template <int STAGE> CPI_DEV void commit(double k, int idx, double* P, double* cur, double* acc, int S, double cs, double dt6) {
+    if (STAGE == 1) { SM(cur, idx) = fma(k, cs, SM(P, idx)); SM(acc, idx) = k; }
+    else if (STAGE < 4) { const double a = SM(acc, idx); SM(cur, idx) = fma(k, cs, SM(P, idx)); SM(acc, idx) = fma(2.0, k, a); }
+    else { SM(P, idx) = fma(dt6, SM(acc, idx) + k, SM(P, idx)); }
+}
+template <int STAGE> CPI_DEV void commit9(const double* k, int off, double* P, double* cur, double* acc, int S, double cs, double dt6) {
+#pragma unroll
+    for (int e = 0; e < 9; e++) commit<STAGE>(k[e], off + e, P, cur, acc, S, cs, dt6);
+}
+
+// One RK4 stage over the whole tile.  src = where this stage's P_s lives (P itself for stage 1, cur otherwise).
+// Blocks are visited in REVERSE dependency order so that cur can be updated in place.
+//   w: w_hat;  A = -R*^T [a_hat x];  B = -R*^T;  C = -R*^T [g_tau x] (model 2);  pgg_s/paa_s: stage values of the scalar blocks.
+template <int STAGE, int MODEL>
+CPI_DEV void rk4_stage(double* P, double* cur, double* acc, int S, const double* w, const double* A, const double* B, const double* C,
+                       double pgg_s, double paa_s, double cs, double dt6, double q_w, double q_a) {
+    const double* src = (STAGE == 1) ? P : cur;
+    double k[9];
+
+    // ---- pp:  k = P_pv + P_pv^T
+    double pv[9];
+    ld9(src, S, PV, pv);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = i; j < 3; j++) commit<STAGE>(pv[3 * i + j] + pv[3 * j + i], PP + sym3(i, j), P, cur, acc, S, cs, dt6);
+
+    // ---- pv:  k = P_vv + P_ptheta A^T + P_pa B^T (+ P_cp^T C^T)
+    double pt[9], pa[9], vv[9];
+    ld9(src, S, PT, pt); ld9(src, S, PA, pa); ldsym(src, S, VV, vv);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double s = vv[3 * i + j];
+#pragma unroll
+            for (int m = 0; m < 3; m++) s = fma(pt[3 * i + m], A[3 * j + m], s);
+#pragma unroll
+            for (int m = 0; m < 3; m++) s = fma(pa[3 * i + m], B[3 * j + m], s);
+            k[3 * i + j] = s;
+        }
+    if (MODEL == 2) {
+        double cp[9];
+        ld9(cur, S, CP, cp);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int m = 0; m < 3; m++) k[3 * i + j] = fma(cp[3 * m + i], C[3 * j + m], k[3 * i + j]);
+        // ---- cp (transient):  k = P_cv ; base value = P_theta,p = P_ptheta^T
+        if (STAGE < 4) {
+            double cv[9];
+            ld9(cur, S, CV, cv);
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) SM(cur, CP + 3 * i + j) = fma(cv[3 * i + j], cs, SM(P, PT + 3 * j + i));
+        }
+    }
+    commit9<STAGE>(k, PV, P, cur, acc, S, cs, dt6);
+
+    // ---- ptheta:  k = P_vtheta + P_ptheta W - P_pg
+    double vt[9], pg[9];
+    ld9(src, S, VT, vt); ld9(src, S, PG, pg);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double c3[3];
+        cross(&pt[3 * i], w, c3);
+#pragma unroll
+        for (int j = 0; j < 3; j++) k[3 * i + j] = vt[3 * i + j] + c3[j] - pg[3 * i + j];
+    }
+    commit9<STAGE>(k, PT, P, cur, acc, S, cs, dt6);
+
+    // ---- pa:  k = P_va        pg:  k = P_vg
+    double va[9], vg[9];
+    ld9(src, S, VA, va); ld9(src, S, VG, vg);
+    commit9<STAGE>(va, PA, P, cur, acc, S, cs, dt6);
+    commit9<STAGE>(vg, PG, P, cur, acc, S, cs, dt6);
+
+    // ---- vv:  k = M + M^T + q_a I,  M = A P_vtheta^T + B P_va^T (+ C P_cv)
+    {
+        double M[9];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                double s = 0.0;
+#pragma unroll
+                for (int m = 0; m < 3; m++) s = fma(A[3 * i + m], vt[3 * j + m], s);
+#pragma unroll
+                for (int m = 0; m < 3; m++) s = fma(B[3 * i + m], va[3 * j + m], s);
+                M[3 * i + j] = s;
+            }
+        if (MODEL == 2) {
+            double cv[9];
+            ld9(cur, S, CV, cv);
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+#pragma unroll
+                    for (int m = 0; m < 3; m++) M[3 * i + j] = fma(C[3 * i + m], cv[3 * m + j], M[3 * i + j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = i; j < 3; j++)
+                commit<STAGE>(M[3 * i + j] + M[3 * j + i] + (i == j ? q_a : 0.0), VV + sym3(i, j), P, cur, acc, S, cs, dt6);
+    }
+
+    double tt[9], tg[9];
+    ldsym(src, S, TT, tt); ld9(src, S, TG, tg);
+
+    if (MODEL == 2) {
+        // ---- cv (transient):  k = P_ctheta A^T + P_cc C^T ;  P_cc = P_theta,theta at step start (constant), base = P_vtheta^T
+        double ct[9];
+        ld9(cur, S, CT, ct);
+        if (STAGE < 4) {
+            double cc[9];
+            ldsym(P, S, TT, cc);
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int m = 0; m < 3; m++) s = fma(ct[3 * i + m], A[3 * j + m], s);
+#pragma unroll
+                    for (int m = 0; m < 3; m++) s = fma(cc[3 * i + m], C[3 * j + m], s);
+                    SM(cur, CV + 3 * i + j) = fma(s, cs, SM(P, VT + 3 * j + i));
+                }
+        }
+        // ---- vtheta:  k = A P_tt + P_vtheta W - P_vg + C P_ctheta
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            double c3[3];
+            cross(&vt[3 * i], w, c3);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                double s = c3[j] - vg[3 * i + j];
+#pragma unroll
+                for (int m = 0; m < 3; m++) s = fma(A[3 * i + m], tt[3 * m + j], s);
+#pragma unroll
+                for (int m = 0; m < 3; m++) s = fma(C[3 * i + m], ct[3 * m + j], s);
+                k[3 * i + j] = s;
+            }
+        }
+        commit9<STAGE>(k, VT, P, cur, acc, S, cs, dt6);
+        // ---- ctheta (transient):  k = P_ctheta W - P_cg ;  P_cg = P_theta,bg at step start (constant), base = P_tt
+        if (STAGE < 4) {
+            double cg[9], bt[9];
+            ld9(P, S, TG, cg); ldsym(P, S, TT, bt);
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                double c3[3];
+                cross(&ct[3 * i], w, c3);
+#pragma unroll
+                for (int j = 0; j < 3; j++) SM(cur, CT + 3 * i + j) = fma(c3[j] - cg[3 * i + j], cs, bt[3 * i + j]);
+            }
+        }
+    } else {
+        // ---- vtheta:  k = A P_tt + P_vtheta W - P_vg
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            double c3[3];
+            cross(&vt[3 * i], w, c3);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                double s = c3[j] - vg[3 * i + j];
+#pragma unroll
+                for (int m = 0; m < 3; m++) s = fma(A[3 * i + m], tt[3 * m + j], s);
+                k[3 * i + j] = s;
+            }
+        }
+        commit9<STAGE>(k, VT, P, cur, acc, S, cs, dt6);
+    }
+
+    // ---- va:  k = paa * B
+#pragma unroll
+    for (int e = 0; e < 9; e++) k[e] = paa_s * B[e];
+    commit9<STAGE>(k, VA, P, cur, acc, S, cs, dt6);
+
+    // ---- vg:  k = A P_tg (+ C P_cg, P_cg = P_theta,bg at step start)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int m = 0; m < 3; m++) s = fma(A[3 * i + m], tg[3 * m + j], s);
+            k[3 * i + j] = s;
+        }
+    if (MODEL == 2) {
+        double cg[9];
+        ld9(P, S, TG, cg);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int m = 0; m < 3; m++) k[3 * i + j] = fma(C[3 * i + m], cg[3 * m + j], k[3 * i + j]);
+    }
+    commit9<STAGE>(k, VG, P, cur, acc, S, cs, dt6);
+
+    // ---- tt:  k = M + M^T + q_w I,  M = -W P_tt - P_tg^T     (-W x = x cross w, column-wise)
+    {
+        double M[9];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double col[3] = {tt[j], tt[3 + j], tt[6 + j]}, c3[3];
+            cross(col, w, c3);
+#pragma unroll
+            for (int i = 0; i < 3; i++) M[3 * i + j] = c3[i] - tg[3 * j + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = i; j < 3; j++)
+                commit<STAGE>(M[3 * i + j] + M[3 * j + i] + (i == j ? q_w : 0.0), TT + sym3(i, j), P, cur, acc, S, cs, dt6);
+    }
+    // ---- tg:  k = -W P_tg - pgg I
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        double col[3] = {tg[j], tg[3 + j], tg[6 + j]}, c3[3];
+        cross(col, w, c3);
+#pragma unroll
+        for (int i = 0; i < 3; i++) k[3 * i + j] = c3[i] - (i == j ? pgg_s : 0.0);
+    }
+    commit9<STAGE>(k, TG, P, cur, acc, S, cs, dt6);
+}
+
+// rows of  -R^T [a x] : row i = a cross r_i  with r_i = column i of R (R row-major)
+CPI_DEV void make_A(const double* R, const double* a, double* A) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const double r[3] = {R[i], R[3 + i], R[6 + i]};
+        cross(a, r, &A[3 * i]);
+    }
+}
+CPI_DEV void make_B(const double* R, double* B) {   // -R^T
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) B[3 * i + j] = -R[3 * j + i];
+}
+
+// I - a W + b W2 applied to R:  out = (I - a [w x] + b [w x]^2) R
+CPI_DEV void rot_apply(double a, double b, const double* w, const double* R, double* out) {
+    const double w00 = -(w[1] * w[1] + w[2] * w[2]), w11 = -(w[0] * w[0] + w[2] * w[2]), w22 = -(w[0] * w[0] + w[1] * w[1]);
+    const double w01 = w[0] * w[1], w02 = w[0] * w[2], w12 = w[1] * w[2];
+    double D[9];
+    D[0] = 1.0 + b * w00;      D[1] = a * w[2] + b * w01; D[2] = -a * w[1] + b * w02;
+    D[3] = -a * w[2] + b * w01; D[4] = 1.0 + b * w11;     D[5] = a * w[0] + b * w12;
+    D[6] = a * w[1] + b * w02;  D[7] = -a * w[0] + b * w12; D[8] = 1.0 + b * w22;
+    mul33(D, R, out);
+}
+
+struct Coef { double f1, f2, f3, f4, d1, d2, d3, d4; };
+// CpiV1.h:132-142, 196-238 (== CpiV2.h:158-168, 231-274)
+CPI_DEV void coefficients(bool small_w, double dt, double mag, double th, double s, double c, Coef& k) {
+    const double dt2 = dt * dt, dt3 = dt2 * dt;
+    if (small_w) {
+        k.f1 = -(dt3 / 3.0); k.f2 = (dt2 * dt2) / 8.0; k.f3 = -(dt2 / 2.0); k.f4 = dt3 / 6.0;
+        k.d1 = -(dt3 * dt2 / 15.0); k.d2 = (dt3 * dt3) / 72.0; k.d3 = -(dt2 * dt2 / 12.0); k.d4 = (dt3 * dt2) / 60.0;
+    } else {
+        const double m2 = mag * mag, m3 = m2 * mag, m4 = m2 * m2, th2 = th * th;
+        k.f1 = (th * c - s) / m3;
+        k.f2 = (th2 - 2.0 * c - 2.0 * th * s + 2.0) / (2.0 * m4);
+        k.f3 = -(1.0 - c) / m2;
+        k.f4 = (th - s) / m3;
+        k.d1 = (th2 * s - 3.0 * s + 3.0 * th * c) / (m4 * mag);
+        k.d2 = (th2 - 4.0 * c - 4.0 * th * s + th2 * c + 4.0) / (m4 * m2);
+        k.d3 = (2.0 * (c - 1.0) + th * s) / m4;
+        k.d4 = (2.0 * th + th * c - 3.0 * s) / (m4 * mag);
+    }
+}
+
+// =====================================================================================================================
+template <int MODEL, bool AVG, bool ANALYTIC>
+__global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
+    extern __shared__ double smem[];
+    const int S = p.wpb;
+    const int tid = threadIdx.x;
+    const int64_t win = (int64_t)blockIdx.x * S + tid;
+    if (tid >= S || win >= p.n_windows) return;
+
+    double* P = smem + tid;
+    double* acc = P + (size_t)NP * S;
+    double* cur = acc + (size_t)NP * S;
+    double* Dj = cur + (size_t)(MODEL == 2 ? NCUR2 : NP) * S;   // model 2 only
+
+    // ---- per-window constants (setLinearizationPoints, CpiBase.h:73-80)
+    const double* lin = p.lin + win * CPI_LIN_DOUBLES;
+    const double bw[3] = {lin[0], lin[1], lin[2]}, ba[3] = {lin[3], lin[4], lin[5]};
+    double g_k[3] = {0, 0, 0};
+    if (MODEL == 2) {
+        const double q[4] = {lin[6], lin[7], lin[8], lin[9]}, g[3] = {lin[10], lin[11], lin[12]};
+        double RG[9];
+        quat_2_Rot(q, RG);
+        mv33(RG, g, g_k);                                // quat_2_Rot(q_k_lin) * grav   (CpiV2.h:99, 202, 315)
+    }
+    int64_t o0, nsteps;
+    if (p.offsets) { o0 = p.offsets[win]; nsteps = p.offsets[win + 1] - o0 - (AVG ? 1 : 0); }
+    else { o0 = win * (p.ns_uniform + (AVG ? 1 : 0)); nsteps = p.ns_uniform; }
+    if (nsteps < 0) nsteps = 0;
+    const double* sp = p.samples + o0 * CPI_SAMPLE_DOUBLES;
+
+    // ---- state (CpiBase.h:99-124 initialisers)
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double alpha[3] = {0, 0, 0}, beta[3] = {0, 0, 0}, DT = 0.0;
+    double Jq[9], Ja[9], Jb[9], Ha[9], Hb[9], Oa[9], Ob[9];
+#pragma unroll
+    for (int e = 0; e < 9; e++) { Jq[e] = Ja[e] = Jb[e] = Ha[e] = Hb[e] = Oa[e] = Ob[e] = 0.0; }
+    double pgg = 0.0, paa = 0.0;
+#pragma unroll 1
+    for (int e = 0; e < NP; e++) SM(P, e) = 0.0;
+    if (MODEL == 2) {
+#pragma unroll 1
+        for (int e = 0; e < ND; e++) SM(Dj, e) = 0.0;
+    }
+
+    // software prefetch of the next entry
+    double nx[7];
+    if (nsteps > 0 || AVG) {
+#pragma unroll
+        for (int e = 0; e < 7; e++) nx[e] = (nsteps > 0 || AVG) ? __ldg(sp + e) : 0.0;
+    }
+
+#pragma unroll 1
+    for (int64_t it = 0; it < nsteps; it++) {
+        double s0[7];
+#pragma unroll
+        for (int e = 0; e < 7; e++) s0[e] = nx[e];
+        if (it + 1 < nsteps + (AVG ? 1 : 0)) {
+#pragma unroll
+            for (int e = 0; e < 7; e++) nx[e] = __ldg(sp + (it + 1) * CPI_SAMPLE_DOUBLES + e);
+        }
+        const double dt = s0[6];
+        DT += dt;                                        // CpiV1.h:69
+        if (dt == 0.0) continue;                         // CpiV1.h:72-74
+
+        // ---- estimated readings (CpiV1.h:77-86; CpiV2.h:98-106)
+        double wh[3] = {s0[0] - bw[0], s0[1] - bw[1], s0[2] - bw[2]};
+        double ah[3] = {s0[3] - ba[0], s0[4] - ba[1], s0[5] - ba[2]};
+        double g_tau[3] = {0, 0, 0};
+        if (MODEL == 2) {
+            mv33(R, g_k, g_tau);                         // R_k2tau * R_G_to_k * grav  (old R)
+            ah[0] -= g_tau[0]; ah[1] -= g_tau[1]; ah[2] -= g_tau[2];
+        }
+        if (AVG) {
+#pragma unroll
+            for (int e = 0; e < 3; e++) { wh[e] += nx[e] - bw[e]; wh[e] = 0.5 * wh[e]; }
+            if (MODEL == 1) {
+#pragma unroll
+                for (int e = 0; e < 3; e++) { ah[e] += nx[3 + e] - ba[e]; ah[e] = 0.5 * ah[e]; }
+            }
+        }
+        const double mag2 = wh[0] * wh[0] + wh[1] * wh[1] + wh[2] * wh[2];
+        const double mag = sqrt(mag2);
+        const double th = mag * dt;
+        const bool small_w = mag < 0.008726646;          // CpiV1.h:101
+        double sn, cs_;
+        sincos(th, &sn, &cs_);
+        double sh, ch;
+        sincos(mag * 0.5 * dt, &sh, &ch);
+
+        // ---- relative rotation, new and mid rotation (CpiV1.h:119-124, 267-269)
+        double R1[9], Rm[9];
+        {
+            const double a1 = small_w ? dt : sn / mag, b1 = small_w ? (dt * dt) / 2.0 : (1.0 - cs_) / (mag * mag);
+            rot_apply(a1, b1, wh, R, R1);
+            const double hd = 0.5 * dt;
+            const double a2 = small_w ? hd : sh / mag, b2 = small_w ? (hd * hd) / 2.0 : (1.0 - ch) / (mag * mag);
+            rot_apply(a2, b2, wh, R, Rm);
+        }
+        if (MODEL == 2 && AVG) {                         // CpiV2.h:146-149: average the LOCAL acceleration with the NEW rotation
+            double g1[3];
+            mv33(R1, g_k, g1);
+#pragma unroll
+            for (int e = 0; e < 3; e++) { ah[e] += nx[3 + e] - ba[e] - g1[e]; ah[e] = 0.5 * ah[e]; }
+        }
+
+        Coef kf;
+        coefficients(small_w, dt, mag, th, sn, cs_, kf);
+
+        // W and W^2 entries
+        const double W2[9] = {-(wh[1] * wh[1] + wh[2] * wh[2]), wh[0] * wh[1], wh[0] * wh[2],
+                              wh[0] * wh[1], -(wh[0] * wh[0] + wh[2] * wh[2]), wh[1] * wh[2],
+                              wh[0] * wh[2], wh[1] * wh[2], -(wh[0] * wh[0] + wh[1] * wh[1])};
+        const double Wm[9] = {0.0, -wh[2], wh[1], wh[2], 0.0, -wh[0], -wh[1], wh[0], 0.0};
+        double aarg[9], barg[9], Hal[9], Hbe[9];
+        {
+            const double hdt2 = (dt * dt) / 2.0;
+#pragma unroll
+            for (int e = 0; e < 9; e++) {
+                aarg[e] = ((e % 4 == 0) ? hdt2 : 0.0) + kf.f1 * Wm[e] + kf.f2 * W2[e];     // CpiV1.h:145
+                barg[e] = ((e % 4 == 0) ? dt : 0.0) + kf.f3 * Wm[e] + kf.f4 * W2[e];       // CpiV1.h:146
+            }
+        }
+        mulT33(R1, aarg, Hal);                            // R_tau12k * alpha_arg
+        mulT33(R1, barg, Hbe);
+        {
+            double t3[3];
+            mv33(Hal, ah, t3);
+#pragma unroll
+            for (int e = 0; e < 3; e++) alpha[e] += beta[e] * dt + t3[e];   // CpiV1.h:153 (old beta)
+            mv33(Hbe, ah, t3);
+#pragma unroll
+            for (int e = 0; e < 3; e++) beta[e] += t3[e];                   // CpiV1.h:154
+        }
+
+        if (MODEL == 1 || ANALYTIC) {
+            // ---- analytic bias Jacobians (CpiV1.h:162-259; CpiV2.h:188-305)
+            double Jsave[9];
+#pragma unroll
+            for (int e = 0; e < 9; e++) Jsave[e] = Jq[e];
+            {
+                const double c1 = small_w ? 0.5 : (1.0 - cs_) / (th * th), c2 = small_w ? (1.0 / 6.0) : (th - sn) / (th * th * th);
+                const double a1 = small_w ? dt : sn / mag, b1 = small_w ? (dt * dt) / 2.0 : (1.0 - cs_) / (mag * mag);
+                double t9[9];
+                rot_apply(a1, b1, wh, Jq, t9);            // R_tau2tau1 * J_q
+                const double ca = c1 * dt, cb = c2 * dt * dt;   // w_tx = dt*W, w_tx^2 = dt^2 W2
+#pragma unroll
+                for (int e = 0; e < 9; e++) Jq[e] = t9[e] + (((e % 4 == 0) ? 1.0 : 0.0) - ca * Wm[e] + cb * W2[e]) * dt;   // CpiV1.h:167
+            }
+#pragma unroll
+            for (int e = 0; e < 9; e++) { Ha[e] -= Hal[e]; Ha[e] += dt * Hb[e]; Hb[e] -= Hbe[e]; }   // CpiV1.h:170-172 (old H_b)
+            if (MODEL == 2) {                              // CpiV2.h:203-205
+                double sk[9] = {0.0, -g_k[2], g_k[1], g_k[2], 0.0, -g_k[0], -g_k[1], g_k[0], 0.0}, t1[9], t2[9];
+                mul33(R, sk, t1);
+                mul33(Hal, t1, t2);
+#pragma unroll
+                for (int e = 0; e < 9; e++) { Oa[e] += dt * Ob[e]; Oa[e] += -t2[e]; }
+                mul33(Hbe, t1, t2);
+#pragma unroll
+                for (int e = 0; e < 9; e++) Ob[e] += -t2[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 9; e++) Ja[e] += Jb[e] * dt;   // CpiV1.h:241 (old J_b)
+            // vectors shared by the three columns
+            double ua[3], ub[3], Wa[3], W2a[3];
+            mv33(aarg, ah, ua); mv33(barg, ah, ub);
+            cross(wh, ah, Wa);                             // W a = w x a
+            cross(wh, Wa, W2a);                            // W^2 a
+#pragma unroll
+            for (int col = 0; col < 3; col++) {
+                const double e3[3] = {col == 0 ? 1.0 : 0.0, col == 1 ? 1.0 : 0.0, col == 2 ? 1.0 : 0.0};
+                const double jc[3] = {Jq[col], Jq[3 + col], Jq[6 + col]};   // NEW J_q e_i
+                double exa[3], exWa[3], Wexa[3], c1v[3], c2v[3], va_[3], vb_[3], o3[3];
+                cross(e3, ah, exa);                        // e_ix a
+                cross(e3, Wa, exWa);                       // e_ix W a
+                cross(wh, exa, Wexa);                      // W e_ix a
+                cross(jc, ua, c1v);                        // [J_q e_i x] (alpha_arg a)
+                cross(jc, ub, c2v);
+                const double wi = wh[col];
+#pragma unroll
+                for (int e = 0; e < 3; e++) {
+                    va_[e] = -c1v[e] + (wi * kf.d1) * Wa[e] - kf.f1 * exa[e] + (wi * kf.d2) * W2a[e] - kf.f2 * (exWa[e] + Wexa[e]);
+                    vb_[e] = -c2v[e] + (wi * kf.d3) * Wa[e] - kf.f3 * exa[e] + (wi * kf.d4) * W2a[e] - kf.f4 * (exWa[e] + Wexa[e]);
+                }
+                mvT33(R1, va_, o3);
+                if (MODEL == 2) {                          // - H_al [J_save e_i x] g_tau   (CpiV2.h:285-293)
+                    const double js[3] = {Jsave[col], Jsave[3 + col], Jsave[6 + col]};
+                    double cg[3], u[3];
+                    cross(js, g_tau, cg);
+                    mv33(Hal, cg, u);
+                    o3[0] -= u[0]; o3[1] -= u[1]; o3[2] -= u[2];
+                }
+                Ja[col] += o3[0]; Ja[3 + col] += o3[1]; Ja[6 + col] += o3[2];
+                mvT33(R1, vb_, o3);
+                if (MODEL == 2) {                          // CpiV2.h:296-305; column 0 carries the reference's "- -" (plus) sign
+                    const double js[3] = {Jsave[col], Jsave[3 + col], Jsave[6 + col]};
+                    double cg[3], u[3];
+                    cross(js, g_tau, cg);
+                    mv33(Hbe, cg, u);
+                    if (col == 0) { o3[0] += u[0]; o3[1] += u[1]; o3[2] += u[2]; }
+                    else { o3[0] -= u[0]; o3[1] -= u[1]; o3[2] -= u[2]; }
+                }
+                Jb[col] += o3[0]; Jb[3 + col] += o3[1]; Jb[6 + col] += o3[2];
+            }
+        }
+
+        // ---- covariance: 4 RK4 stages on the block-sparse Lyapunov operator (CpiV1.h:272-353; CpiV2.h:326-422)
+        const double hdt = dt / 2.0, dt6 = dt / 6.0;
+        double A[9], B[9], C[9];
+        if (MODEL == 2) {
+            // clone rows start as copies of the theta rows (B_k of the previous step, CpiV2.h:436-441)
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    SM(cur, CT + 3 * i + j) = SM(P, TT + sym3(i, j));
+                    SM(cur, CV + 3 * i + j) = SM(P, VT + 3 * j + i);
+                    SM(cur, CP + 3 * i + j) = SM(P, PT + 3 * j + i);
+                }
+        }
+        make_A(R, ah, A); make_B(R, B);
+        if (MODEL == 2) make_A(R, g_tau, C);
+        rk4_stage<1, MODEL>(P, cur, acc, S, wh, A, B, C, pgg, paa, hdt, dt6, p.q_w, p.q_a);
+        make_A(Rm, ah, A); make_B(Rm, B);
+        if (MODEL == 2) make_A(Rm, g_tau, C);
+        {
+            const double pgg2 = fma(p.q_wb, hdt, pgg), paa2 = fma(p.q_ab, hdt, paa);
+            rk4_stage<2, MODEL>(P, cur, acc, S, wh, A, B, C, pgg2, paa2, hdt, dt6, p.q_w, p.q_a);
+            rk4_stage<3, MODEL>(P, cur, acc, S, wh, A, B, C, pgg2, paa2, dt, dt6, p.q_w, p.q_a);
+        }
+        double A1[9], C1[9];
+        if (MODEL == 2 && !ANALYTIC) {
+#pragma unroll
+            for (int e = 0; e < 9; e++) { A1[e] = A[e]; C1[e] = C[e]; }   // keep the mid-point blocks for Phi
+        }
+        make_A(R1, ah, A); make_B(R1, B);
+        if (MODEL == 2) make_A(R1, g_tau, C);
+        {
+            const double pgg4 = fma(p.q_wb, dt, pgg), paa4 = fma(p.q_ab, dt, paa);
+            rk4_stage<4, MODEL>(P, cur, acc, S, wh, A, B, C, pgg4, paa4, dt, dt6, p.q_w, p.q_a);
+        }
+        pgg += dt6 * (p.q_wb + 2.0 * p.q_wb + 2.0 * p.q_wb + p.q_wb);
+        paa += dt6 * (p.q_ab + 2.0 * p.q_ab + 2.0 * p.q_ab + p.q_ab);
+
+        if (MODEL == 2 && !ANALYTIC) {
+            // ---- Discrete_J_b <- B_k * Phi * Discrete_J_b restricted to the consumed columns (CpiV2.h:347-426, 443).
+            // Phi's RK4 (Phi_dot = F Phi, Phi(0) = I) in block form; stage matrices F1 (R_old), F2 = F3 (R_mid), F4 (R_new).
+            // Row theta:  X' = -W X (- I for the bg column).   Row v: sum_s A_s X_theta,s + B_s/C_s/L_s.   Row p: integral of row v.
+            double A0[9], C0[9];
+            make_A(R, ah, A0); make_A(R, g_tau, C0);
+            // theta-theta and theta-bg columns of Phi, with stage values
+            double Xtt[4][9], Xtg[4][9];   // stage VALUES Phi_s (s = 1..4) of the two theta-row blocks
+            double ktt[4][9], ktg[4][9];   // stage DERIVATIVES
+#pragma unroll
+            for (int e = 0; e < 9; e++) { Xtt[0][e] = (e % 4 == 0) ? 1.0 : 0.0; Xtg[0][e] = 0.0; }
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    double col[3] = {Xtt[s][j], Xtt[s][3 + j], Xtt[s][6 + j]}, c3[3];
+                    cross(col, wh, c3);
+                    ktt[s][j] = c3[0]; ktt[s][3 + j] = c3[1]; ktt[s][6 + j] = c3[2];
+                    double col2[3] = {Xtg[s][j], Xtg[s][3 + j], Xtg[s][6 + j]};
+                    cross(col2, wh, c3);
+                    ktg[s][j] = c3[0] - (j == 0 ? 1.0 : 0.0); ktg[s][3 + j] = c3[1] - (j == 1 ? 1.0 : 0.0); ktg[s][6 + j] = c3[2] - (j == 2 ? 1.0 : 0.0);
+                }
+                if (s < 3) {
+                    const double cstep = (s == 2) ? dt : hdt;
+#pragma unroll
+                    for (int e = 0; e < 9; e++) {
+                        Xtt[s + 1][e] = ((e % 4 == 0) ? 1.0 : 0.0) + ktt[s][e] * cstep;
+                        Xtg[s + 1][e] = ktg[s][e] * cstep;
+                    }
+                }
+            }
+            double Ptt[9], Ptg[9];   // Phi_theta,theta, Phi_theta,bg
+#pragma unroll
+            for (int e = 0; e < 9; e++) {
+                Ptt[e] = ((e % 4 == 0) ? 1.0 : 0.0) + dt6 * (ktt[0][e] + 2.0 * ktt[1][e] + 2.0 * ktt[2][e] + ktt[3][e]);
+                Ptg[e] = dt6 * (ktg[0][e] + 2.0 * ktg[1][e] + 2.0 * ktg[2][e] + ktg[3][e]);
+            }
+            // v-row derivative blocks per stage: kv_X,s = A_s Phi_thetaX,s (+ direct block for the identity rows)
+            const double* As[4] = {A0, A1, A1, A};
+            const double* Cs[4] = {C0, C1, C1, C};
+            double B0[9], Bm[9];
+            make_B(R, B0); make_B(Rm, Bm);
+            const double* Bs[4] = {B0, Bm, Bm, B};
+            // L_s = -R_s^T R_old [g_k x]  (CpiV2.h:336)
+            double L[4][9];
+            {
+                double sk[9] = {0.0, -g_k[2], g_k[1], g_k[2], 0.0, -g_k[0], -g_k[1], g_k[0], 0.0}, RS[9];
+                mul33(R, sk, RS);
+                double t9[9];
+                mulT33(R, RS, t9);
+#pragma unroll
+                for (int e = 0; e < 9; e++) L[0][e] = -t9[e];
+                mulT33(Rm, RS, t9);
+#pragma unroll
+                for (int e = 0; e < 9; e++) { L[1][e] = -t9[e]; L[2][e] = -t9[e]; }
+                mulT33(R1, RS, t9);
+#pragma unroll
+                for (int e = 0; e < 9; e++) L[3][e] = -t9[e];
+            }
+            double kvt[4][9], kvg[4][9];
+#pragma unroll
+            for (int s = 0; s < 4; s++) { mul33(As[s], Xtt[s], kvt[s]); mul33(As[s], Xtg[s], kvg[s]); }
+            // Phi_v,X = dt/6 (k1 + 2k2 + 2k3 + k4);  Phi_p,X = dt/6 (X1 + 2 X2 + 2 X3 + X4) with X_s the v-row stage VALUES:
+            // X1 = 0, X2 = hdt k1, X3 = hdt k2, X4 = dt k3
+            double Pvt[9], Pvg[9], Pva[9], Pvc[9], Pvl[9], Ppt[9], Ppg[9], Ppa[9], Ppc[9], Ppl[9];
+#pragma unroll
+            for (int e = 0; e < 9; e++) {
+                Pvt[e] = dt6 * (kvt[0][e] + 2.0 * kvt[1][e] + 2.0 * kvt[2][e] + kvt[3][e]);
+                Pvg[e] = dt6 * (kvg[0][e] + 2.0 * kvg[1][e] + 2.0 * kvg[2][e] + kvg[3][e]);
+                Pva[e] = dt6 * (Bs[0][e] + 2.0 * Bs[1][e] + 2.0 * Bs[2][e] + Bs[3][e]);
+                Pvc[e] = dt6 * (Cs[0][e] + 2.0 * Cs[1][e] + 2.0 * Cs[2][e] + Cs[3][e]);
+                Pvl[e] = dt6 * (L[0][e] + 2.0 * L[1][e] + 2.0 * L[2][e] + L[3][e]);
+                Ppt[e] = dt6 * (2.0 * (kvt[0][e] * hdt) + 2.0 * (kvt[1][e] * hdt) + kvt[2][e] * dt);
+                Ppg[e] = dt6 * (2.0 * (kvg[0][e] * hdt) + 2.0 * (kvg[1][e] * hdt) + kvg[2][e] * dt);
+                Ppa[e] = dt6 * (2.0 * (Bs[0][e] * hdt) + 2.0 * (Bs[1][e] * hdt) + Bs[2][e] * dt);
+                Ppc[e] = dt6 * (2.0 * (Cs[0][e] * hdt) + 2.0 * (Cs[1][e] * hdt) + Cs[2][e] * dt);
+                Ppl[e] = dt6 * (2.0 * (L[0][e] * hdt) + 2.0 * (L[1][e] * hdt) + L[2][e] * dt);
+            }
+            const double Ppv = dt6 * (1.0 + 2.0 + 2.0 + 1.0);   // Phi_p,v = that * I
+            // apply: D' = B_k Phi D on columns {bg, ba, theta_klin}; D_c,X == D_theta,X (clone of the previous step)
+            double Dtg[9], Dvg[9], Dpg[9], Dva[9], Dpa[9], Dvl[9], Dpl[9], n1[9], n2[9], n3[9];
+            ld9(Dj, S, D_TG, Dtg); ld9(Dj, S, D_VG, Dvg); ld9(Dj, S, D_PG, Dpg);
+            ld9(Dj, S, D_VA, Dva); ld9(Dj, S, D_PA, Dpa); ld9(Dj, S, D_VL, Dvl); ld9(Dj, S, D_PL, Dpl);
+            double Pvtc[9], Pptc[9];
+#pragma unroll
+            for (int e = 0; e < 9; e++) { Pvtc[e] = Pvt[e] + Pvc[e]; Pptc[e] = Ppt[e] + Ppc[e]; }
+            mul33(Ptt, Dtg, n1); mul33(Pvtc, Dtg, n2); mul33(Pptc, Dtg, n3);
+#pragma unroll
+            for (int e = 0; e < 9; e++) {
+                const double dpg = n3[e] + Ppg[e] + Ppv * Dvg[e] + Dpg[e];
+                const double dvg = n2[e] + Pvg[e] + Dvg[e];
+                const double dtg = n1[e] + Ptg[e];
+                const double dpa = Ppa[e] + Ppv * Dva[e] + Dpa[e];
+                const double dva = Pva[e] + Dva[e];
+                const double dpl = Ppl[e] + Ppv * Dvl[e] + Dpl[e];
+                const double dvl = Pvl[e] + Dvl[e];
+                SM(Dj, D_TG + e) = dtg; SM(Dj, D_VG + e) = dvg; SM(Dj, D_PG + e) = dpg;
+                SM(Dj, D_VA + e) = dva; SM(Dj, D_PA + e) = dpa; SM(Dj, D_VL + e) = dvl; SM(Dj, D_PL + e) = dpl;
+            }
+        }
+
+        // ---- commit rotation (CpiV1.h:357)
+#pragma unroll
+        for (int e = 0; e < 9; e++) R[e] = R1[e];
+    }
+
+    // ---- write the record (column-major 3x3 / 15x15, include/cpi_b200.h)
+    constexpr int RD = (MODEL == 1) ? CPI_REC_V1_DOUBLES : CPI_REC_V2_DOUBLES;
+    double* rec = p.out + win * (int64_t)RD;
+    {
+        double q[4];
+        rot_2_quat(R, q);                                  // CpiV1.h:358 (only the last one is ever consumed)
+        rec[CPI_REC_Q] = q[0]; rec[CPI_REC_Q + 1] = q[1]; rec[CPI_REC_Q + 2] = q[2]; rec[CPI_REC_Q + 3] = q[3];
+    }
+    if (MODEL == 2 && !ANALYTIC) {                         // CpiV2.h:450-458
+        double t[9];
+        ld9(Dj, S, D_TG, t);
+#pragma unroll
+        for (int e = 0; e < 9; e++) Jq[e] = -t[e];
+        ld9(Dj, S, D_PG, Ja); ld9(Dj, S, D_VG, Jb); ld9(Dj, S, D_PA, Ha); ld9(Dj, S, D_VA, Hb); ld9(Dj, S, D_PL, Oa); ld9(Dj, S, D_VL, Ob);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            rec[CPI_REC_R + i + 3 * j] = R[3 * i + j];
+            rec[CPI_REC_JQ + i + 3 * j] = Jq[3 * i + j];
+            rec[CPI_REC_JA + i + 3 * j] = Ja[3 * i + j];
+            rec[CPI_REC_JB + i + 3 * j] = Jb[3 * i + j];
+            rec[CPI_REC_HA + i + 3 * j] = Ha[3 * i + j];
+            rec[CPI_REC_HB + i + 3 * j] = Hb[3 * i + j];
+            if (MODEL == 2) { rec[CPI_REC_OA + i + 3 * j] = Oa[3 * i + j]; rec[CPI_REC_OB + i + 3 * j] = Ob[3 * i + j]; }
+        }
+#pragma unroll
+    for (int e = 0; e < 3; e++) { rec[CPI_REC_ALPHA + e] = alpha[e]; rec[CPI_REC_BETA + e] = beta[e]; }
+    rec[CPI_REC_DT] = DT;
+    // P_meas, full 15x15: block (I,J), I,J in {theta=0,bg=1,v=2,ba=3,p=4}
+    double* Pm = rec + CPI_REC_P;
+    auto put = [&](int r, int c, double v) { Pm[r + 15 * c] = v; };
+#pragma unroll 1
+    for (int i = 0; i < 3; i++)
+#pragma unroll 1
+        for (int j = 0; j < 3; j++) {
+            const int sidx = sym3(i, j);
+            put(i, j, SM(P, TT + sidx));            put(6 + i, 6 + j, SM(P, VV + sidx));      put(12 + i, 12 + j, SM(P, PP + sidx));
+            put(3 + i, 3 + j, i == j ? pgg : 0.0);  put(9 + i, 9 + j, i == j ? paa : 0.0);
+            put(i, 9 + j, 0.0); put(9 + j, i, 0.0); put(3 + i, 9 + j, 0.0); put(9 + j, 3 + i, 0.0);
+            double v;
+            v = SM(P, TG + 3 * i + j); put(i, 3 + j, v);      put(3 + j, i, v);
+            v = SM(P, VT + 3 * i + j); put(6 + i, j, v);      put(j, 6 + i, v);
+            v = SM(P, VG + 3 * i + j); put(6 + i, 3 + j, v);  put(3 + j, 6 + i, v);
+            v = SM(P, VA + 3 * i + j); put(6 + i, 9 + j, v);  put(9 + j, 6 + i, v);
+            v = SM(P, PT + 3 * i + j); put(12 + i, j, v);     put(j, 12 + i, v);
+            v = SM(P, PG + 3 * i + j); put(12 + i, 3 + j, v); put(3 + j, 12 + i, v);
+            v = SM(P, PV + 3 * i + j); put(12 + i, 6 + j, v); put(6 + j, 12 + i, v);
+            v = SM(P, PA + 3 * i + j); put(12 + i, 9 + j, v); put(9 + j, 12 + i, v);
+        }
+}
+
+// ---- host-side launcher (called from capi.cu) --------------------------------------------------------------------------
+template <int MODEL, bool AVG, bool ANALYTIC>
+static cudaError_t launch_one(const PreintParams& p, int grid, int block, size_t smem, cudaStream_t st) {
+    auto kern = k_preintegrate<MODEL, AVG, ANALYTIC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, block, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// Windows per block.  Small batches: spread over all SMs in ONE wave (a second wave would double the latency of a
+// latency-bound launch).  Large batches: as many windows as the SM's shared memory holds, in whole warps.
+int preint_pick_wpb(int model, int64_t n_windows, int num_sms, int max_smem_bytes) {
+    const int per_win = tile_doubles(model) * 8;
+    int fit = max_smem_bytes / per_win;
+    if (fit > 128) fit = 128;
+    if (fit < 1) fit = 1;
+    const int64_t need = (n_windows + num_sms - 1) / num_sms;
+    if (need <= fit) return (int)(need < 1 ? 1 : need);
+    return fit >= 32 ? fit / 32 * 32 : fit;
+}
+
+cudaError_t preint_launch(int model, int flags, const PreintParams& p0, int num_sms, int max_smem_bytes, cudaStream_t st, int* launches) {
+    PreintParams p = p0;
+    if (p.n_windows == 0) return cudaSuccess;
+    p.wpb = preint_pick_wpb(model, p.n_windows, num_sms, max_smem_bytes);
+    const int block = (p.wpb + 31) / 32 * 32;
+    const int64_t grid64 = (p.n_windows + p.wpb - 1) / p.wpb;
+    const size_t smem = (size_t)tile_doubles(model) * 8 * p.wpb;
+    const int grid = (int)grid64;
+    const bool avg = flags & CPI_FLAG_IMU_AVG, ana = flags & CPI_FLAG_ANALYTIC_JACOBIANS;
+    cudaError_t e;
+    if (model == 1) e = avg ? launch_one<1, true, false>(p, grid, block, smem, st) : launch_one<1, false, false>(p, grid, block, smem, st);
+    else if (!ana) e = avg ? launch_one<2, true, false>(p, grid, block, smem, st) : launch_one<2, false, false>(p, grid, block, smem, st);
+    else e = avg ? launch_one<2, true, true>(p, grid, block, smem, st) : launch_one<2, false, true>(p, grid, block, smem, st);
+    if (launches) *launches = 1;
+    return e;
+}
+
+}  // namespace cpi

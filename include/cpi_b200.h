@@ -1,0 +1,153 @@
+/*
+ * cpi_b200.h -- C ABI of libcpi_b200.so: batched closed-form IMU preintegration (CPI) on B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the ONE hot path of rpng/cpi (reference tree paths are relative to
+ * /root/reference/cpi_compare/src):
+ *
+ *   cpi_preintegrate_batch*    replaces the per-sample loop  CpiV1::feed_IMU  (cpi/CpiV1.h:62-361) and
+ *                              CpiV2::feed_IMU (cpi/CpiV2.h:84-467) as driven, once per factor, by
+ *                              GraphSolver::createimufactor_cpi_v1/_v2 (solvers/GraphSolver_IMU.cpp:43-75, 97-130),
+ *                              for MANY windows at once.  Its per-window output record is exactly the set of public
+ *                              CpiBase fields the caller reads afterwards (cpi/CpiBase.h:99-124, cpi/CpiV2.h:62-63).
+ *   cpi_imu_factor_eval_batch* replaces ImuFactorCPIv1::evaluateError (gtsam/ImuFactorCPIv1.cpp:37-208) and
+ *                              ImuFactorCPIv2::evaluateError (gtsam/ImuFactorCPIv2.cpp:38-212): unwhitened 15-d
+ *                              residual and the two 15x15 Jacobians, for many factors at once.
+ *   cpi_predict_state_batch*   replaces GraphSolver::getpredictedstate_v1/_v2 (solvers/GraphSolver_IMU.cpp:263-307).
+ *   cpi_retract_batch*         replaces JPLNavState::retract (gtsam/JPLNavState.cpp:37-71).
+ *
+ * Conventions (all identical to the reference):  fp64; matrices COLUMN-major (Eigen default); JPL quaternion
+ * [x y z w]; 15-d error-state order [dtheta(0:3), b_g(3:6), v/beta(6:9), b_a(9:12), p/alpha(12:15)]
+ * (cpi/CpiV1.h:277-281, gtsam/ImuFactorCPIv1.cpp:80-88).
+ *
+ * Functions without the _host suffix take DEVICE pointers and enqueue on `stream` (a cudaStream_t passed as
+ * void*; NULL = legacy default stream) without synchronising.  *_host variants take HOST pointers, stage through
+ * pinned buffers owned by the library, and return after the results are in the caller's buffers.
+ * Every function returns CPI_OK (0) or a negative CPI_E* code; cpi_last_error() gives the message of the last
+ * failure on the calling thread.  (The reference has no error convention for this path: feed_IMU returns void and
+ * never checks its inputs -- CpiBase.h:86.)  No function falls back to a CPU implementation.
+ */
+#ifndef CPI_B200_H
+#define CPI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- layouts -------------------------------------------------------------------------------------------------- */
+
+/* One IMU entry: [wx wy wz ax ay az dt] ; dt = t_{i+1} - t_i (seconds) is the length of the step that STARTS at this
+ * entry, i.e. feed_IMU(t_i, t_i + dt, w_i, a_i, w_{i+1}, a_{i+1}).  The reference's line format "wx wy wz ax ay az
+ * <unused> t_ms" (sim/SimParser.h:148-175) maps to this after differencing the time stamps. */
+#define CPI_SAMPLE_DOUBLES 7
+/* Per-window linearisation point = arguments of CpiBase::setLinearizationPoints (cpi/CpiBase.h:73-80):
+ * [b_w_lin(3) b_a_lin(3) q_k_lin(4, JPL xyzw) grav(3)].  Model 1 ignores q_k_lin for preintegration; grav is only
+ * carried to the factor (GraphSolver_IMU.cpp:74). */
+#define CPI_LIN_DOUBLES 13
+/* JPLNavState value (gtsam/JPLNavState.h:62-66): [q_GtoI(4) b_g(3) v_IinG(3) b_a(3) p_IinG(3)] */
+#define CPI_STATE_DOUBLES 16
+
+/* Per-window result record, doubles.  Field order = order the factor constructors consume them
+ * (gtsam/ImuFactorCPIv1.h:78-81, gtsam/ImuFactorCPIv2.h:82-85). */
+#define CPI_REC_Q      0    /* q_k2tau  [4]  rot_2_quat(R_k2tau)            CpiBase.h:102 */
+#define CPI_REC_R      4    /* R_k2tau  [9]  col-major                      CpiBase.h:103 */
+#define CPI_REC_ALPHA  13   /* alpha_tau[3]                                 CpiBase.h:100 */
+#define CPI_REC_BETA   16   /* beta_tau [3]                                 CpiBase.h:101 */
+#define CPI_REC_DT     19   /* DT                                           CpiBase.h:99  */
+#define CPI_REC_JQ     20   /* J_q [9]  d(theta)/d(b_w)                     CpiBase.h:106 */
+#define CPI_REC_JA     29   /* J_a [9]  d(alpha)/d(b_w)                     CpiBase.h:107 */
+#define CPI_REC_JB     38   /* J_b [9]  d(beta)/d(b_w)                      CpiBase.h:108 */
+#define CPI_REC_HA     47   /* H_a [9]  d(alpha)/d(b_a)                     CpiBase.h:109 */
+#define CPI_REC_HB     56   /* H_b [9]  d(beta)/d(b_a)                      CpiBase.h:110 */
+#define CPI_REC_P      65   /* P_meas [225] col-major 15x15                 CpiBase.h:124 */
+#define CPI_REC_V1_DOUBLES 290
+#define CPI_REC_OA     290  /* O_a [9]  d(alpha)/d(theta_k_lin)  (model 2)  CpiV2.h:62 */
+#define CPI_REC_OB     299  /* O_b [9]  d(beta)/d(theta_k_lin)   (model 2)  CpiV2.h:63 */
+#define CPI_REC_V2_DOUBLES 308
+
+/* flags */
+#define CPI_FLAG_IMU_AVG             1  /* CpiBase::imu_avg = true (CpiBase.h:95); each window then carries ONE extra
+                                           trailing entry whose (w,a) are the "_1" arguments of the last step */
+#define CPI_FLAG_ANALYTIC_JACOBIANS  2  /* model 2 only: state_transition_jacobians = false (CpiV2.h:58); default
+                                           (flag clear) is the reference's default/true path (GraphSolver_IMU.cpp:100) */
+
+/* error codes */
+#define CPI_OK          0
+#define CPI_EINVAL     -1   /* bad argument (NULL pointer, unknown model/dtype, negative count) */
+#define CPI_ECUDA      -2   /* a CUDA runtime call failed; see cpi_last_error() */
+#define CPI_ENODEVICE  -3   /* no CUDA device / not an sm_100 device */
+#define CPI_ENOMEM     -4
+
+/* ---- preintegration ---------------------------------------------------------------------------------------------- */
+
+/*
+ * Preintegrate n_windows independent windows.
+ *   model          1 (CpiV1) or 2 (CpiV2)
+ *   dtype          64 (fp64; samples/lin/records are double) or 32 (fp32 storage: float samples/lin/records,
+ *                  see DESIGN.md for the mixed-precision rule)
+ *   sample_offsets device int64[n_windows+1], entry index (not bytes) of each window's first entry in `samples`;
+ *                  or NULL for uniform windows of `ns_uniform` steps laid out back to back.
+ *                  Window w has  steps = offsets[w+1]-offsets[w]  (minus 1 if CPI_FLAG_IMU_AVG).
+ *   samples        device, CPI_SAMPLE_DOUBLES per entry
+ *   lin            device, CPI_LIN_DOUBLES per window
+ *   sigmas         HOST double[4] = {sigma_w, sigma_wb, sigma_a, sigma_ab}  (CpiBase ctor, CpiBase.h:52-57)
+ *   out_records    device, CPI_REC_V1_DOUBLES (model 1) or CPI_REC_V2_DOUBLES (model 2) per window
+ * A window with zero steps yields the reference's freshly constructed object: R = I, everything else 0
+ * (q_k2tau is uninitialised in the reference, CpiBase.h:102; this library writes [0 0 0 1]).
+ */
+int cpi_preintegrate_batch(int model, int dtype, int64_t n_windows,
+                           const int64_t* sample_offsets, int64_t ns_uniform,
+                           const void* samples, const void* lin, const double* sigmas, int flags,
+                           void* out_records, void* stream);
+
+/* Same with HOST buffers: pinned staging + H2D + kernel + D2H, synchronous.  sample_offsets is a HOST array. */
+int cpi_preintegrate_batch_host(int model, int dtype, int64_t n_windows,
+                                const int64_t* sample_offsets, int64_t ns_uniform,
+                                const void* samples, const void* lin, const double* sigmas, int flags,
+                                void* out_records);
+
+/* ---- factor evaluation ------------------------------------------------------------------------------------------- */
+
+/*
+ * Evaluate n IMU factors.  Factor f links states[idx_i[f]] -> states[idx_j[f]] (idx arrays may be NULL: then
+ * idx_i[f] = f, idx_j[f] = f+1, the reference's chain X(k),X(k+1) -- GraphSolver_IMU.cpp:74) and uses
+ * records[f] / lin[f] (the window's record and linearisation point, i.e. the factor's constructor arguments).
+ *   e   device double[n*15]            residual  [2*q_r(0:3); bg_j-bg_i; betahat-beta; ba_j-ba_i; alphahat-alpha]
+ *   H1  device double[n*225] col-major d e / d x_i   (may be NULL)
+ *   H2  device double[n*225] col-major d e / d x_j   (may be NULL)
+ * Unwhitened, exactly what evaluateError returns; the Gaussian::Covariance(P_meas) whitening lives in GTSAM.
+ */
+int cpi_imu_factor_eval_batch(int model, int64_t n_factors,
+                              const double* states, const int64_t* idx_i, const int64_t* idx_j,
+                              const double* records, const double* lin,
+                              double* e, double* H1, double* H2, void* stream);
+
+int cpi_imu_factor_eval_batch_host(int model, int64_t n_factors, int64_t n_states,
+                                   const double* states, const int64_t* idx_i, const int64_t* idx_j,
+                                   const double* records, const double* lin,
+                                   double* e, double* H1, double* H2);
+
+/* ---- callers either side of the factor ("next" rows) ----------------------------------------------------------------- */
+
+/* x_{k+1} prediction from x_k and a record: getpredictedstate_v1/_v2 (GraphSolver_IMU.cpp:263-307).
+ * states_k / states_k1: device, CPI_STATE_DOUBLES per window. */
+int cpi_predict_state_batch(int model, int64_t n, const double* states_k, const double* records, const double* lin,
+                            double* states_k1, void* stream);
+
+/* JPLNavState::retract (JPLNavState.cpp:37-71): states_out[i] = states[i] (+) xi[i], xi = 15 doubles each. */
+int cpi_retract_batch(int64_t n, const double* states, const double* xi, double* states_out, void* stream);
+
+/* ---- misc ----------------------------------------------------------------------------------------------------------- */
+
+const char* cpi_last_error(void);
+const char* cpi_version(void);
+int cpi_record_doubles(int model);          /* 290 or 308; CPI_EINVAL otherwise */
+int cpi_device_count(void);                 /* number of usable sm_100 devices, or negative error */
+/* number of kernel launches issued by this library on the calling process since load (for bench.py's gpu_launches) */
+int64_t cpi_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPI_B200_H */

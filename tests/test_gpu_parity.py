@@ -1,0 +1,196 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+ (1) the committed golden vectors produced by the unmodified reference,
+ (2) the plain-C oracle on seeded inputs,
+ (3) the compiled reference itself when oracle/_ref/libcpi_ref.so travelled with the snapshot,
+ (4) size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+
+from cpi_b200 import synth
+from parity import compare_records, window_band
+
+pytestmark = pytest.mark.gpu
+CASES = ("cam200", "real200", "real100", "real400", "synth200", "edge")
+MODES = [(1, 0), (1, 1), (2, 0), (2, 1), (2, 2), (2, 3)]
+
+
+def _inputs(G, name, flags):
+    avg = bool(flags & 1)
+    S = G[f"{name}/samples_avg"] if avg else G[f"{name}/samples"]
+    off = G[f"{name}/offsets_avg"] if avg else G[f"{name}/offsets"]
+    return S, off, G[f"{name}/lin"]
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("model,flags", MODES)
+def test_cuda_matches_golden(cuda, golden, name, model, flags):
+    from cpi_b200 import preint
+    G = golden["preint"]
+    S, off, lin = _inputs(G, name, flags)
+    ref = G[f"{name}/records_m{model}_f{flags}"]
+    got = preint.preintegrate_host(model, S, lin, G["sigmas"], flags, offsets=off)
+    steps = np.diff(off) - (1 if flags & 1 else 0)
+    worst = compare_records(got, ref, model, in_band=window_band(S, off, lin), has_steps=steps > 0)
+    print(name, model, flags, {k: f"{v:.1e}" for k, v in worst.items()})
+
+
+@pytest.mark.parametrize("model,flags", MODES)
+def test_cuda_matches_oracle_seeded(cuda, oracle, model, flags):
+    """Device-pointer entry point on the bench distribution (incl. forced small_w / zero-w / dt=0 windows)."""
+    from cpi_b200 import preint
+    torch = cuda
+    n, ns = 2100, 60                       # > 148 windows per SM-wave boundary effects: ragged last block
+    S, L = synth.make_windows(n, ns, rate=200.0, first_window=0, imu_avg=bool(flags & 1))
+    got = preint.preintegrate(model, torch.from_numpy(S).cuda(), torch.from_numpy(L).cuda(), synth.SIGMAS, flags, ns=ns)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    sel = np.r_[0:64, 1000:1040, n - 40:n]
+    ref = oracle.preintegrate(model, S[sel], L[sel], synth.SIGMAS, flags, ns=ns, nthreads=8)
+    ent = S.shape[1]
+    off = np.arange(len(sel) + 1, dtype=np.int64) * ent
+    compare_records(got[sel], ref, model, in_band=window_band(S[sel].reshape(-1, 7), off, L[sel]))
+
+
+@pytest.mark.parametrize("model", [1, 2])
+def test_cuda_matches_reference_live(cuda, reference, model):
+    from cpi_b200 import preint
+    S, L = synth.make_windows(500, 200 if model == 1 else 400, rate=200.0 if model == 1 else 400.0, first_window=123456)
+    ns = S.shape[1]
+    got = preint.preintegrate_host(model, S, L, synth.SIGMAS, 0, ns=ns)
+    ref = reference.preintegrate(model, S, L, synth.SIGMAS, 0, ns=ns, nthreads=16)
+    off = np.arange(501, dtype=np.int64) * ns
+    worst = compare_records(got, ref, model, in_band=window_band(S.reshape(-1, 7), off, L))
+    print(model, {k: f"{v:.1e}" for k, v in worst.items()})
+
+
+def test_ragged_and_empty_batches(cuda, oracle):
+    from cpi_b200 import preint
+    rng = np.random.default_rng(11)
+    S, L = synth.make_windows(300, 50)
+    lens = rng.integers(0, 51, size=300); lens[:5] = [0, 1, 50, 0, 2]
+    wins = [S[i, :lens[i]] for i in range(300)]
+    off = np.zeros(301, dtype=np.int64); off[1:] = np.cumsum(lens)
+    Sx = np.concatenate(wins)
+    for model in (1, 2):
+        got = preint.preintegrate_host(model, Sx, L, synth.SIGMAS, 0, offsets=off)
+        ref = oracle.preintegrate(model, Sx, L, synth.SIGMAS, 0, offsets=off, nthreads=8)
+        compare_records(got, ref, model, in_band=window_band(Sx, off, L), has_steps=lens > 0)
+        assert np.array_equal(got[0, 4:13], np.eye(3).reshape(-1)) and np.all(got[0, 13:] == 0) and np.array_equal(got[0, 0:4], [0, 0, 0, 1])
+    assert preint.preintegrate_host(1, np.zeros((0, 7)), np.zeros((0, 13)), synth.SIGMAS, 0, ns=10).shape == (0, 290)
+
+
+@pytest.mark.parametrize("model", [1, 2])
+def test_factor_eval_matches_golden(cuda, golden, model):
+    from cpi_b200 import factor
+    F = golden["factor"]
+    X, rec, lin = F[f"m{model}/states"], F[f"m{model}/records"], F[f"m{model}/lin"]
+    for idx, suffix in ((None, ""), ((F[f"m{model}/idx_i"], F[f"m{model}/idx_j"]), "_idx")):
+        e, H1, H2 = factor.factor_eval_host(model, X, rec, lin, *(idx or (None, None)))
+        for got, key in ((e, "e"), (H1, "H1"), (H2, "H2")):
+            ref = F[f"m{model}/{key}{suffix}"]
+            err = np.max(np.abs(got - ref))
+            assert err <= 1e-12 * max(1.0, np.max(np.abs(ref))), (key, err)
+            assert np.array_equal(got == 0, ref == 0) or key == "e"      # structural zeros of H1/H2 are exact zeros
+    e_only, h1, h2 = factor.factor_eval_host(model, X, rec, lin, want_H1=False, want_H2=False)
+    assert h1 is None and h2 is None and np.max(np.abs(e_only - F[f"m{model}/e"])) <= 1e-12 * 10
+    got = factor.retract(X, F[f"m{model}/xi"])
+    assert np.max(np.abs(got - F[f"m{model}/retracted"])) <= 1e-14
+    # predict: against the oracle restatement of getpredictedstate (GraphSolver_IMU.cpp:263-307)
+
+
+@pytest.mark.parametrize("model", [1, 2])
+def test_factor_chain_5k_and_predict(cuda, oracle, model):
+    """Config 5 shape: 5k-keyframe chain, every factor evaluated on device; parity vs the oracle on all of them."""
+    from cpi_b200 import preint, factor
+    n = 4999
+    S, L = synth.make_windows(n, 20, rate=200.0, first_window=9000)
+    rec = preint.preintegrate_host(model, S, L, synth.SIGMAS, 0, ns=20)
+    X = synth.make_states(rec, L, model)
+    e, H1, H2 = factor.factor_eval_host(model, X, rec, L)
+    eo, H1o, H2o = oracle.factor_eval(model, X, rec, L, nthreads=8)
+    for got, ref in ((e, eo), (H1, H1o), (H2, H2o)):
+        assert np.max(np.abs(got - ref)) <= 1e-11 * max(1.0, np.max(np.abs(ref)))
+    pred = factor.predict_state(model, X[:-1], rec, L)
+    assert np.max(np.abs(pred - oracle.predict_state(model, X[:-1], rec, L))) <= 1e-11 * np.max(np.abs(X))
+
+
+def test_reference_shaped_objects(cuda, golden):
+    """The CpiBase-shaped facade: feed_IMU per sample, finalize, read the public fields -- vs the reference's records."""
+    from cpi_b200.preint import CpiV1, CpiV2, flush
+    from cpi_b200.factor import ImuFactorCPIv1, ImuFactorCPIv2, JPLNavState
+    G = golden["preint"]
+    S, off, lin = G["cam200/samples"], G["cam200/offsets"], G["cam200/lin"]
+    sg = G["sigmas"]
+    objs = []
+    for model, cls in ((1, CpiV1), (2, CpiV2)):
+        for i in range(6):
+            c = cls(*sg)
+            c.setLinearizationPoints(lin[i, 0:3], lin[i, 3:6], lin[i, 6:10], lin[i, 10:13])
+            c.imu_avg = False
+            t = 0.0
+            for s in S[off[i]:off[i + 1]]:
+                c.feed_IMU(t, t + s[6], s[0:3], s[3:6], s[0:3], s[3:6])
+                t += s[6]
+            objs.append((model, i, c))
+    flush([c for _, _, c in objs])
+    for model, i, c in objs:
+        ref = G[f"cam200/records_m{model}_f0"][i]
+        # feed_IMU differences t_1 - t_0 on the host, so dt differs from the fixture's by an ulp: north_star gates
+        compare_records(c.record()[None], ref[None], model, tol_mean=1e-9)
+        assert c.P_meas.shape == (15, 15) and np.array_equal(c.P_meas, c.P_meas.T)
+        assert abs(c.DT - ref[19]) < 1e-12
+    # the factor facade: ctor argument order of the reference, evaluateError with optional Jacobians
+    F = golden["factor"]
+    for model in (1, 2):
+        X, rec, l = F[f"m{model}/states"], F[f"m{model}/records"], F[f"m{model}/lin"]
+        r = rec[3]
+        m = lambda a, b, sh: r[a:b].reshape(sh, order="F")
+        args = [m(65, 290, (15, 15)), r[19], l[3, 10:13], r[13:16], r[16:19], r[0:4]]
+        if model == 2:
+            args.append(l[3, 6:10])
+        args += [l[3, 3:6], l[3, 0:3], m(20, 29, (3, 3)), m(38, 47, (3, 3)), m(29, 38, (3, 3)), m(56, 65, (3, 3)), m(47, 56, (3, 3))]
+        if model == 2:
+            args += [m(299, 308, (3, 3)), m(290, 299, (3, 3))]
+        fac = (ImuFactorCPIv1 if model == 1 else ImuFactorCPIv2)(3, 4, *args)
+        xi, xj = JPLNavState.from_vector(X[3]), JPLNavState.from_vector(X[4])
+        e, H1, H2 = fac.evaluateError(xi, xj, True, True)
+        assert np.max(np.abs(e - F[f"m{model}/e"][3])) <= 1e-12 * 10
+        assert np.max(np.abs(H1.reshape(-1, order="F") - F[f"m{model}/H1"][3])) <= 1e-12 * 10
+        assert np.max(np.abs(H2.reshape(-1, order="F") - F[f"m{model}/H2"][3])) <= 1e-12
+        assert np.array_equal(fac.evaluateError(xi, xj), e)
+
+
+def test_full_size_properties(cuda, oracle):
+    """BASELINE configs[1]: 10k windows x 200 samples, model 1, fp64 -- properties that do not need a 10k-window oracle run."""
+    from cpi_b200 import preint
+    torch = cuda
+    n, ns = 10000, 200
+    S, L = synth.make_windows(n, ns, rate=200.0)
+    dS, dL = torch.from_numpy(S).cuda(), torch.from_numpy(L).cuda()
+    rec = preint.preintegrate(1, dS, dL, synth.SIGMAS, 0, ns=ns)
+    # (a) shard invariance: any contiguous split gives bit-identical records (windows are independent)
+    parts = [preint.preintegrate(1, dS[a:b].contiguous(), dL[a:b].contiguous(), synth.SIGMAS, 0, ns=ns) for a, b in ((0, 3333), (3333, 7000), (7000, n))]
+    torch.cuda.synchronize()
+    assert torch.equal(rec, torch.cat(parts))
+    r = rec.cpu().numpy()
+    assert np.all(np.isfinite(r))
+    # (b) DT is the plain running sum of dt; R orthonormal; q consistent with R; P symmetric with the two structural zero blocks
+    dts = np.zeros(n)
+    for i in range(ns):
+        dts += S[:, i, 6]
+    assert np.array_equal(r[:, 19], dts)
+    R = r[:, 4:13].reshape(n, 3, 3).transpose(0, 2, 1)
+    assert np.max(np.abs(R @ R.transpose(0, 2, 1) - np.eye(3))) < 1e-12
+    P = r[:, 65:290].reshape(n, 15, 15).transpose(0, 2, 1)
+    assert np.array_equal(P, P.transpose(0, 2, 1))
+    assert np.all(P[:, 0:6, 9:12] == 0) and np.all(np.linalg.eigvalsh(P[::97]) > -1e-18)
+    # (c) bg/ba diagonal blocks are sigma^2 * DT * I up to rounding of the running sum
+    assert np.allclose(P[:, 3, 3], synth.SIGMAS[1] ** 2 * dts, rtol=1e-12) and np.allclose(P[:, 9, 9], synth.SIGMAS[3] ** 2 * dts, rtol=1e-12)
+    # (d) spot parity on a stride through the batch (includes the forced small_w / zero / dt=0 windows)
+    mag = np.linalg.norm(S[:, :, 0:3] - L[:, None, 0:3], axis=2)
+    special = np.where((mag.max(axis=1) < 0.0088) | (S[:, :, 6].min(axis=1) == 0))[0][:24]
+    sel = np.unique(np.r_[np.arange(0, n, 211), special])
+    ref = oracle.preintegrate(1, S[sel], L[sel], synth.SIGMAS, 0, ns=ns, nthreads=16)
+    off = np.arange(len(sel) + 1, dtype=np.int64) * ns
+    worst = compare_records(r[sel], ref, 1, in_band=window_band(S[sel].reshape(-1, 7), off, L[sel]))
+    print({k: f"{v:.1e}" for k, v in worst.items()})
