@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- IMU windows/sec of the batched closed-form preintegration hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload v1_10k_200|v2_100k_400]
+
+One "step" = one pass of the hot path over one batch of synthetic IMU windows (cpi_b200/synth.py, seed 20260924).
+Default workload = BASELINE.json configs[1]: 10 000 windows x 200 samples, CPI model 1 (mean + Jacobians + covariance),
+fp64, per GPU.  With N > 1 every rank preintegrates its own 10k-window shard (weak scaling, windows are independent) and
+the step ends with ONE NCCL all-gather of the result records, the kernel having written its shard straight into its
+slice of the gather buffer.  Timing: W untimed warm-up steps, then K steps between barrier + synchronize, CUDA events on
+the launching stream, max over ranks.  Inputs rotate over several distinct resident batches whose total size exceeds
+the 126 MB L2, so no step finds its samples in cache.
+
+Extra keys: roofline (dominant kernel vs the measured fp64 DFMA peak and vs measured HBM bandwidth), cpu_baseline (the
+reference's own CPU implementation timed on this box's host cores, rank 0, N = 1), e2e (same metric through the C-ABI
+host entry point with pinned HOST buffers: H2D + kernel + D2H inside the timed region), clocks, gpu_launches.
+`--impl reference` times the reference's CPU path (oracle/_ref when it was compiled, else the oracle port) on all host
+threads on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model, windows per GPU, samples per window, rate Hz, algorithmic flops/sample, bytes/window in+out)  SURVEY 8(d)
+    "v1_10k_200": dict(model=1, n=10_000, ns=200, rate=200.0, flops_per_sample=5.8e3, bytes_per_window=13_624,
+                       desc="configs[1]: 10k-window batch x 200 samples, CPI v1 mean+covariance, fp64"),
+    "v2_100k_400": dict(model=2, n=100_000, ns=400, rate=400.0, flops_per_sample=15.0e3, bytes_per_window=24_968,
+                        desc="configs[2]: 100k-window batch x 400 samples, CPI v2, fp64"),
+}
+DFMA_PEAK_TFLOPS = 34.17   # measured on this pool's B200 by tools/microbench.cu (profiles/microbench_r01.jsonl), burst == sustained
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index; self.rows = []; self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.05:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_arm(wl, sample_windows, nthreads=None):
+    """The reference's own CPU implementation of the path on the host cores: (value windows/s, kind, cores, sample)."""
+    from oracle.oracle import Oracle, Reference
+    from cpi_b200 import synth
+    if Reference.available():
+        impl, kind = Reference(), "reference"
+    else:
+        if not os.path.exists(Oracle.path):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "liboracle.so"], check=True)
+        impl, kind = Oracle(), "port"
+    cores = nthreads or os.cpu_count() or 1
+    S, L = synth.make_windows(sample_windows, wl["ns"], rate=wl["rate"])
+    impl.preintegrate(wl["model"], S[:cores], L[:cores], synth.SIGMAS, 0, ns=wl["ns"], nthreads=cores)   # warm
+    t0 = time.perf_counter()
+    impl.preintegrate(wl["model"], S, L, synth.SIGMAS, 0, ns=wl["ns"], nthreads=cores)
+    dt = time.perf_counter() - t0
+    return sample_windows / dt, kind, cores, dt
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # bounded sample: calibrate on a small run, then size each step for ~5 s of CPU work (all host threads)
+    v0, kind, cores, _ = cpu_arm(wl, max(2 * cores, 64))
+    sample = int(min(wl["n"], max(cores, v0 * 5.0)))
+    times = []
+    for i in range(args.warmup + args.steps):
+        v, kind, cores, dt = cpu_arm(wl, sample)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms * 1e-3)
+    line = {"impl": "reference", "metric": "imu_windows_per_sec", "value": value, "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": wl["desc"], "windows_per_step": sample, "samples_per_window": wl["ns"], "model": f"CpiV{wl['model']}"},
+            "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": kind,
+                             "sample": f"{sample} windows x {wl['ns']} samples per step, {'oracle/_ref (unmodified reference, std::thread over windows)' if kind == 'reference' else 'oracle C port'}"},
+            "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="v1_10k_200", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+    import torch.distributed as dist
+    from cpi_b200 import capi, preint, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    capi.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    model, n, ns = wl["model"], wl["n"], wl["ns"]
+    rd = capi.REC_DOUBLES[model]
+
+    # ---- resident inputs: NB distinct batches, NB * bytes > L2
+    bytes_in = n * ns * 56 + n * 104
+    NB = max(2, int(np.ceil(300e6 / bytes_in)))
+    if bytes_in > 300e6:
+        NB = 2
+    batches = []
+    for b in range(NB):
+        S, L = synth.make_windows(n, ns, rate=wl["rate"], first_window=(rank * NB + b) * n)
+        batches.append((torch.from_numpy(S).to(dev), torch.from_numpy(L).to(dev)))
+    gather = torch.empty((world, n, rd), dtype=torch.float64, device=dev)     # rank r's kernel writes gather[r] in place
+    mine = gather[rank]
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        S, L = batches[i % NB]
+        preint.preintegrate(model, S, L, synth.SIGMAS, 0, ns=ns, out=mine, stream=stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gather.view(-1), mine.view(-1))
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.15)
+    launches0 = capi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t0 = time.time()
+    ev0.record(stream)
+    for i in range(args.steps):
+        S, L = batches[(args.warmup + i) % NB]
+        kev[i][0].record(stream)
+        preint.preintegrate(model, S, L, synth.SIGMAS, 0, ns=ns, out=mine, stream=stream)
+        kev[i][1].record(stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gather.view(-1), mine.view(-1))
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    t1 = time.time()
+    if world > 1:
+        dist.barrier()
+    launches = capi.launch_count() - launches0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    total_ms = ev0.elapsed_time(ev1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    out = None
+    if rank == 0:
+        peaks, how = measured_peaks()
+        flops = wl["flops_per_sample"] * ns * n          # algorithmic flops per launch (SURVEY 8d contract)
+        ach_tf = flops / (kern_ms * 1e-3) * 1e-12
+        ach_gbs = wl["bytes_per_window"] * n / (kern_ms * 1e-3) * 1e-9
+        out = {"metric": "imu_windows_per_sec", "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": wl["desc"], "windows_per_gpu": n, "samples_per_window": ns, "model": f"CpiV{model}",
+                          "parallelism": f"window-sharded x{world}" + (", one NCCL all-gather of records per step" if world > 1 else ""),
+                          "l2": f"{NB} rotating resident input batches = {NB * bytes_in / 1e6:.0f} MB > 126 MB L2"},
+               "gpu_launches": int(launches),
+               "kernel_ms": kern_ms,
+               "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": DFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach_tf / DFMA_PEAK_TFLOPS,
+                            "traffic": None,
+                            "note": "fp64 CUDA-core (DFMA) bound, not HBM/tensor: 85 flop/B; peak = DFMA microbenchmark measured on this pool "
+                                    "(tools/microbench.cu, profiles/microbench_r01.jsonl); achieved = algorithmic flops (5.8 kflop/sample v1, 15 v2) / kernel time",
+                            "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"], "peak_source": how}},
+               "clocks": clocks}
+
+    # ---- e2e through the C-ABI host entry point, pinned host buffers, H2D + kernel + D2H inside the timed region
+    if not args.no_e2e:
+        S, L = synth.make_windows(n, ns, rate=wl["rate"], first_window=rank * n)
+        hS = torch.from_numpy(S).pin_memory(); hL = torch.from_numpy(L).pin_memory()
+        hO = torch.empty((n, rd), dtype=torch.float64).pin_memory()
+        sig = np.ascontiguousarray(synth.SIGMAS)
+        lib = capi.load()
+        import ctypes
+
+        def host_step():
+            capi.check(lib.cpi_preintegrate_batch_host(model, 64, n, None, ns, ctypes.c_void_p(hS.data_ptr()), ctypes.c_void_p(hL.data_ptr()),
+                                                       ctypes.c_void_p(sig.ctypes.data), 0, ctypes.c_void_p(hO.data_ptr())))
+        for _ in range(3):
+            host_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ke = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            host_step()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / ke
+        if world > 1:
+            t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        if rank == 0:
+            out["e2e"] = {"value": world * n / (e2e_ms * 1e-3), "unit": "windows/s", "ms_per_step": e2e_ms,
+                          "h2d_bytes_per_step": int(hS.numel() * 8 + hL.numel() * 8), "d2h_bytes_per_step": int(hO.numel() * 8),
+                          "api": "cpi_preintegrate_batch_host (C ABI, pinned host buffers)"}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v0, kind, cores, _ = cpu_arm(wl, max(2 * cores, 64))
+        sample = int(min(wl["n"], max(cores, v0 * 10.0)))
+        v, kind, cores, dt = cpu_arm(wl, sample)
+        out["cpu_baseline"] = {"value": v, "unit": "windows/s", "cores": cores, "kind": kind,
+                               "sample": f"{sample} windows x {ns} samples of the same synthetic workload, {dt:.1f} s, "
+                                         + ("unmodified reference headers (oracle/_ref), std::thread over windows" if kind == "reference" else "oracle C port")}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
