@@ -135,12 +135,13 @@ def run_reference(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="v1_10k_200", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="debug: do not poll nvidia-smi during the timed region")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -174,34 +175,46 @@ def main():
     for b in range(NB):
         S, L = synth.make_windows(n, ns, rate=wl["rate"], first_window=(rank * NB + b) * n)
         batches.append((torch.from_numpy(S).to(dev), torch.from_numpy(L).to(dev)))
+    del S, L      # NB: dropping a 112 MB numpy array is a ~12 ms munmap on the host -- must not happen inside the timed loop
     gather = torch.empty((world, n, rd), dtype=torch.float64, device=dev)     # rank r's kernel writes gather[r] in place
     mine = gather[rank]
     stream = torch.cuda.current_stream()
 
     def step(i):
-        S, L = batches[i % NB]
-        preint.preintegrate(model, S, L, synth.SIGMAS, 0, ns=ns, out=mine, stream=stream)
+        dS, dL = batches[i % NB]
+        preint.preintegrate(model, dS, dL, synth.SIGMAS, 0, ns=ns, out=mine, stream=stream)
         if world > 1:
             dist.all_gather_into_tensor(gather.view(-1), mine.view(-1))
 
-    for i in range(args.warmup):
-        step(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+    # everything host-side (events, clock sampler) is set up BEFORE the warm-up so that the GPU goes from the warm-up
+    # steps straight into the timed region without an idle gap (see DESIGN.md "measurement notes").
+    sampler = ClockSampler(torch.cuda.current_device()) if (rank == 0 and not args.no_clocks) else None
     if sampler:
-        sampler.start(); time.sleep(0.15)
-    launches0 = capi.launch_count()
+        sampler.start(); time.sleep(0.3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e in [ev0, ev1] + [x for pair in kev for x in pair]:
+        e.record(stream)                     # force the lazy cudaEventCreate now
+    # clock settle: the part idles at 120 MHz while the host generates inputs and needs ~20 ms of work (with a ~13 ms
+    # P-state stall in it, measured) to reach its load clocks; keep it busy for >= 150 ms before the W warm-up steps
+    t_settle = time.perf_counter()
+    while time.perf_counter() - t_settle < 0.15:
+        step(0)
+        torch.cuda.synchronize()
+    for i in range(args.warmup):
+        step(i)
+    launches0 = capi.launch_count()
+    import gc
+    gc.collect(); gc.disable()        # no collector pauses inside the timed region
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     t0 = time.time()
     ev0.record(stream)
     for i in range(args.steps):
-        S, L = batches[(args.warmup + i) % NB]
+        dS, dL = batches[(args.warmup + i) % NB]
         kev[i][0].record(stream)
-        preint.preintegrate(model, S, L, synth.SIGMAS, 0, ns=ns, out=mine, stream=stream)
+        preint.preintegrate(model, dS, dL, synth.SIGMAS, 0, ns=ns, out=mine, stream=stream)
         kev[i][1].record(stream)
         if world > 1:
             dist.all_gather_into_tensor(gather.view(-1), mine.view(-1))
@@ -211,9 +224,14 @@ def main():
     if world > 1:
         dist.barrier()
     launches = capi.launch_count() - launches0
+    gc.enable()
     clocks = sampler.stop(t0, t1) if sampler else None
     total_ms = ev0.elapsed_time(ev1)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    if os.environ.get("CPI_BENCH_DEBUG"):
+        print("kernel ms:", [round(a.elapsed_time(b), 3) for a, b in kev], file=sys.stderr)
+        print("gaps ms:", [round(kev[i][1].elapsed_time(kev[i + 1][0]), 3) for i in range(len(kev) - 1)], file=sys.stderr)
+        print("head/tail ms:", round(ev0.elapsed_time(kev[0][0]), 3), round(kev[-1][1].elapsed_time(ev1), 3), file=sys.stderr)
     if world > 1:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

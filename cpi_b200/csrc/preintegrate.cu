@@ -23,7 +23,7 @@
 
 namespace cpi {
 
-// ---- shared-memory tile layout (unique entries of P_meas; units: doubles per window) --------------------------------
+// ---- shared-memory tile layout (units: doubles per window; element e of window w lives at tile[e * S + w]) ----------
 enum : int {
     TT = 0,   // P_theta,theta  sym 6
     TG = 6,   // P_theta,bg     9   (i = theta row, j = bg col)
@@ -42,110 +42,151 @@ enum : int {
     CV = 99,  // P_c,v     9
     CP = 108, // P_c,p     9
     NCUR2 = 117,
-    // model 2 only: the non-trivial blocks of Discrete_J_b in the consumed columns (bg, ba, theta_klin)
-    D_TG = 0, D_VG = 9, D_PG = 18, D_VA = 27, D_PA = 36, D_VL = 45, D_PL = 54, ND = 63
+    // model 2, default mode: the non-trivial blocks of Discrete_J_b in the consumed columns (bg, ba, theta_klin)
+    D_TG = 0, D_VG = 9, D_PG = 18, D_VA = 27, D_PA = 36, D_VL = 45, D_PL = 54, ND = 63,
+    // analytic Jacobian state (model 1; model 2 with CPI_FLAG_ANALYTIC_JACOBIANS): same 63-double region
+    J_Q = 0, J_A = 9, J_B = 18, H_A = 27, H_B = 36, O_A = 45, O_B = 54,
+    // TMA staging: two buffers of one 128-byte line (+16 B pad against bank conflicts) per window, NOT element-major
+    BUF_DOUBLES = 18
 };
 
-__host__ __device__ constexpr int tile_doubles(int model) { return model == 1 ? (NP * 3) : (NP * 2 + NCUR2 + ND); }
+// Per-model tile description.  S (window stride == max windows per CTA) is a compile-time constant so that every
+// shared-memory access is [base + immediate]; it is chosen as large as 227 KB allow.
+template <int MODEL> struct Tile;
+template <> struct Tile<1> {
+    static constexpr int NCUR = NP, NJ = 45, S = 80;
+    static constexpr int OFF_ACC = NP, OFF_CUR = 2 * NP, OFF_J = 3 * NP, ELEMS = 3 * NP + NJ;     // 315 element-major doubles
+};
+template <> struct Tile<2> {
+    static constexpr int NCUR = NCUR2, NJ = ND, S = 72;
+    static constexpr int OFF_ACC = NP, OFF_CUR = 2 * NP, OFF_J = 2 * NP + NCUR2, ELEMS = 2 * NP + NCUR2 + ND;   // 360
+};
+template <int MODEL> __host__ __device__ constexpr size_t tile_bytes() {
+    // element-major part + per-window staging buffers (2 x 18 doubles) + 2 mbarriers
+    return (size_t)Tile<MODEL>::S * (Tile<MODEL>::ELEMS + 2 * BUF_DOUBLES + 2) * sizeof(double);
+}
 
+// ---- TMA (1-D bulk copy) + mbarrier primitives: SASS UBLKCP / SYNCS ---------------------------------------------------
+CPI_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+CPI_DEV void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+CPI_DEV void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+CPI_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+CPI_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+CPI_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- block loaders ----------------------------------------------------------------------------------------------------
 #define SM(buf, idx) (buf)[(idx) * S]
 
-CPI_DEV void ld9(const double* b, int S, int off, double* x) {
+template <int S> CPI_DEV void ld9(const double* b, int off, double* x) {
 #pragma unroll
     for (int k = 0; k < 9; k++) x[k] = SM(b, off + k);
 }
-CPI_DEV void ldsym(const double* b, int S, int off, double* x) {   // packed sym -> full row-major 3x3
+template <int S> CPI_DEV void ldsym(const double* b, int off, double* x) {   // packed sym -> full row-major 3x3
     const double a0 = SM(b, off), a1 = SM(b, off + 1), a2 = SM(b, off + 2), a3 = SM(b, off + 3), a4 = SM(b, off + 4), a5 = SM(b, off + 5);
     x[0] = a0; x[1] = a1; x[2] = a2; x[3] = a1; x[4] = a3; x[5] = a4; x[6] = a2; x[7] = a4; x[8] = a5;
 }
 
 // RK4 bookkeeping for one entry.  Reference: P2 = P + k1*dt/2, P3 = P + k2*dt/2, P4 = P + k3*dt,
 // P += (dt/6)*(k1 + 2 k2 + 2 k3 + k4)   (CpiV1.h:312, 323, 344, 352).
-template <int STAGE> CPI_DEV void commit(double k, int idx, double* P, double* cur, double* acc, int S, double cs, double dt6) {
+template <int STAGE, int S> CPI_DEV void commit(double k, int idx, double* P, double* cur, double* acc, double cs, double dt6) {
     if (STAGE == 1) { SM(cur, idx) = fma(k, cs, SM(P, idx)); SM(acc, idx) = k; }
     else if (STAGE < 4) { const double a = SM(acc, idx); SM(cur, idx) = fma(k, cs, SM(P, idx)); SM(acc, idx) = fma(2.0, k, a); }
     else { SM(P, idx) = fma(dt6, SM(acc, idx) + k, SM(P, idx)); }
 }
-template <int STAGE> CPI_DEV void commit9(const double* k, int off, double* P, double* cur, double* acc, int S, double cs, double dt6) {
+template <int STAGE, int S> CPI_DEV void commit9(const double* k, int off, double* P, double* cur, double* acc, double cs, double dt6) {
 #pragma unroll
-    for (int e = 0; e < 9; e++) commit<STAGE>(k[e], off + e, P, cur, acc, S, cs, dt6);
+    for (int e = 0; e < 9; e++) commit<STAGE, S>(k[e], off + e, P, cur, acc, cs, dt6);
 }
 
 // One RK4 stage over the whole tile.  src = where this stage's P_s lives (P itself for stage 1, cur otherwise).
-// Blocks are visited in REVERSE dependency order so that cur can be updated in place.
+// Blocks are visited in REVERSE dependency order so that cur can be updated in place; every section loads just the
+// blocks it needs (LDS with immediate offsets) and is fenced from its neighbours with a compiler barrier so that the
+// scheduler does not hoist a whole stage's loads to the top and spill (the tile is the spill space by design).
 //   w: w_hat;  A = -R*^T [a_hat x];  B = -R*^T;  C = -R*^T [g_tau x] (model 2);  pgg_s/paa_s: stage values of the scalar blocks.
-template <int STAGE, int MODEL>
-CPI_DEV void rk4_stage(double* P, double* cur, double* acc, int S, const double* w, const double* A, const double* B, const double* C,
+#define CPI_SECTION() asm volatile("" ::: "memory")
+template <int STAGE, int MODEL, int S>
+CPI_DEV void rk4_stage(double* P, double* cur, double* acc, const double* w, const double* A, const double* B, const double* C,
                        double pgg_s, double paa_s, double cs, double dt6, double q_w, double q_a) {
     const double* src = (STAGE == 1) ? P : cur;
     double k[9];
 
-    // ---- pp:  k = P_pv + P_pv^T
-    double pv[9];
-    ld9(src, S, PV, pv);
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = i; j < 3; j++) commit<STAGE>(pv[3 * i + j] + pv[3 * j + i], PP + sym3(i, j), P, cur, acc, S, cs, dt6);
-
-    // ---- pv:  k = P_vv + P_ptheta A^T + P_pa B^T (+ P_cp^T C^T)
-    double pt[9], pa[9], vv[9];
-    ld9(src, S, PT, pt); ld9(src, S, PA, pa); ldsym(src, S, VV, vv);
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            double s = vv[3 * i + j];
-#pragma unroll
-            for (int m = 0; m < 3; m++) s = fma(pt[3 * i + m], A[3 * j + m], s);
-#pragma unroll
-            for (int m = 0; m < 3; m++) s = fma(pa[3 * i + m], B[3 * j + m], s);
-            k[3 * i + j] = s;
-        }
-    if (MODEL == 2) {
-        double cp[9];
-        ld9(cur, S, CP, cp);
+    {   // ---- pp:  k = P_pv + P_pv^T
+        double pv[9];
+        ld9<S>(src, PV, pv);
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
-            for (int j = 0; j < 3; j++)
+            for (int j = i; j < 3; j++) commit<STAGE, S>(pv[3 * i + j] + pv[3 * j + i], PP + sym3(i, j), P, cur, acc, cs, dt6);
+    }
+    CPI_SECTION();
+    {   // ---- pv:  k = P_vv + P_ptheta A^T + P_pa B^T (+ P_cp^T C^T)
+        double pt[9], pa[9], vv[9];
+        ld9<S>(src, PT, pt); ld9<S>(src, PA, pa); ldsym<S>(src, VV, vv);
 #pragma unroll
-                for (int m = 0; m < 3; m++) k[3 * i + j] = fma(cp[3 * m + i], C[3 * j + m], k[3 * i + j]);
-        // ---- cp (transient):  k = P_cv ; base value = P_theta,p = P_ptheta^T
-        if (STAGE < 4) {
-            double cv[9];
-            ld9(cur, S, CV, cv);
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                double s = vv[3 * i + j];
+#pragma unroll
+                for (int m = 0; m < 3; m++) s = fma(pt[3 * i + m], A[3 * j + m], s);
+#pragma unroll
+                for (int m = 0; m < 3; m++) s = fma(pa[3 * i + m], B[3 * j + m], s);
+                k[3 * i + j] = s;
+            }
+        if (MODEL == 2) {
+            double cp[9];
+            ld9<S>(cur, CP, cp);
 #pragma unroll
             for (int i = 0; i < 3; i++)
 #pragma unroll
-                for (int j = 0; j < 3; j++) SM(cur, CP + 3 * i + j) = fma(cv[3 * i + j], cs, SM(P, PT + 3 * j + i));
+                for (int j = 0; j < 3; j++)
+#pragma unroll
+                    for (int m = 0; m < 3; m++) k[3 * i + j] = fma(cp[3 * m + i], C[3 * j + m], k[3 * i + j]);
+            // ---- cp (transient):  k = P_cv ; base value = P_theta,p = P_ptheta^T
+            if (STAGE < 4) {
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++) SM(cur, CP + 3 * i + j) = fma(SM(cur, CV + 3 * i + j), cs, SM(P, PT + 3 * j + i));
+            }
         }
+        commit9<STAGE, S>(k, PV, P, cur, acc, cs, dt6);
     }
-    commit9<STAGE>(k, PV, P, cur, acc, S, cs, dt6);
-
-    // ---- ptheta:  k = P_vtheta + P_ptheta W - P_pg
-    double vt[9], pg[9];
-    ld9(src, S, VT, vt); ld9(src, S, PG, pg);
+    CPI_SECTION();
+    {   // ---- ptheta:  k = P_vtheta + P_ptheta W - P_pg
+        double pt[9], vt[9], pg[9];
+        ld9<S>(src, PT, pt); ld9<S>(src, VT, vt); ld9<S>(src, PG, pg);
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-        double c3[3];
-        cross(&pt[3 * i], w, c3);
+        for (int i = 0; i < 3; i++) {
+            double c3[3];
+            cross(&pt[3 * i], w, c3);
 #pragma unroll
-        for (int j = 0; j < 3; j++) k[3 * i + j] = vt[3 * i + j] + c3[j] - pg[3 * i + j];
+            for (int j = 0; j < 3; j++) k[3 * i + j] = vt[3 * i + j] + c3[j] - pg[3 * i + j];
+        }
+        commit9<STAGE, S>(k, PT, P, cur, acc, cs, dt6);
     }
-    commit9<STAGE>(k, PT, P, cur, acc, S, cs, dt6);
-
-    // ---- pa:  k = P_va        pg:  k = P_vg
-    double va[9], vg[9];
-    ld9(src, S, VA, va); ld9(src, S, VG, vg);
-    commit9<STAGE>(va, PA, P, cur, acc, S, cs, dt6);
-    commit9<STAGE>(vg, PG, P, cur, acc, S, cs, dt6);
-
-    // ---- vv:  k = M + M^T + q_a I,  M = A P_vtheta^T + B P_va^T (+ C P_cv)
-    {
-        double M[9];
+    CPI_SECTION();
+    {   // ---- pa:  k = P_va        pg:  k = P_vg
+        double va[9];
+        ld9<S>(src, VA, va);
+        commit9<STAGE, S>(va, PA, P, cur, acc, cs, dt6);
+        ld9<S>(src, VG, va);
+        commit9<STAGE, S>(va, PG, P, cur, acc, cs, dt6);
+    }
+    CPI_SECTION();
+    {   // ---- vv:  k = M + M^T + q_a I,  M = A P_vtheta^T + B P_va^T (+ C P_cv)
+        double vt[9], va[9], M[9];
+        ld9<S>(src, VT, vt); ld9<S>(src, VA, va);
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -159,7 +200,7 @@ CPI_DEV void rk4_stage(double* P, double* cur, double* acc, int S, const double*
             }
         if (MODEL == 2) {
             double cv[9];
-            ld9(cur, S, CV, cv);
+            ld9<S>(cur, CV, cv);
 #pragma unroll
             for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -171,106 +212,101 @@ CPI_DEV void rk4_stage(double* P, double* cur, double* acc, int S, const double*
         for (int i = 0; i < 3; i++)
 #pragma unroll
             for (int j = i; j < 3; j++)
-                commit<STAGE>(M[3 * i + j] + M[3 * j + i] + (i == j ? q_a : 0.0), VV + sym3(i, j), P, cur, acc, S, cs, dt6);
+                commit<STAGE, S>(M[3 * i + j] + M[3 * j + i] + (i == j ? q_a : 0.0), VV + sym3(i, j), P, cur, acc, cs, dt6);
     }
-
-    double tt[9], tg[9];
-    ldsym(src, S, TT, tt); ld9(src, S, TG, tg);
-
-    if (MODEL == 2) {
+    CPI_SECTION();
+    if (MODEL == 2 && STAGE < 4) {
         // ---- cv (transient):  k = P_ctheta A^T + P_cc C^T ;  P_cc = P_theta,theta at step start (constant), base = P_vtheta^T
-        double ct[9];
-        ld9(cur, S, CT, ct);
-        if (STAGE < 4) {
-            double cc[9];
-            ldsym(P, S, TT, cc);
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int m = 0; m < 3; m++) s = fma(ct[3 * i + m], A[3 * j + m], s);
-#pragma unroll
-                    for (int m = 0; m < 3; m++) s = fma(cc[3 * i + m], C[3 * j + m], s);
-                    SM(cur, CV + 3 * i + j) = fma(s, cs, SM(P, VT + 3 * j + i));
-                }
-        }
-        // ---- vtheta:  k = A P_tt + P_vtheta W - P_vg + C P_ctheta
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            double c3[3];
-            cross(&vt[3 * i], w, c3);
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                double s = c3[j] - vg[3 * i + j];
-#pragma unroll
-                for (int m = 0; m < 3; m++) s = fma(A[3 * i + m], tt[3 * m + j], s);
-#pragma unroll
-                for (int m = 0; m < 3; m++) s = fma(C[3 * i + m], ct[3 * m + j], s);
-                k[3 * i + j] = s;
-            }
-        }
-        commit9<STAGE>(k, VT, P, cur, acc, S, cs, dt6);
-        // ---- ctheta (transient):  k = P_ctheta W - P_cg ;  P_cg = P_theta,bg at step start (constant), base = P_tt
-        if (STAGE < 4) {
-            double cg[9], bt[9];
-            ld9(P, S, TG, cg); ldsym(P, S, TT, bt);
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                double c3[3];
-                cross(&ct[3 * i], w, c3);
-#pragma unroll
-                for (int j = 0; j < 3; j++) SM(cur, CT + 3 * i + j) = fma(c3[j] - cg[3 * i + j], cs, bt[3 * i + j]);
-            }
-        }
-    } else {
-        // ---- vtheta:  k = A P_tt + P_vtheta W - P_vg
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            double c3[3];
-            cross(&vt[3 * i], w, c3);
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                double s = c3[j] - vg[3 * i + j];
-#pragma unroll
-                for (int m = 0; m < 3; m++) s = fma(A[3 * i + m], tt[3 * m + j], s);
-                k[3 * i + j] = s;
-            }
-        }
-        commit9<STAGE>(k, VT, P, cur, acc, S, cs, dt6);
-    }
-
-    // ---- va:  k = paa * B
-#pragma unroll
-    for (int e = 0; e < 9; e++) k[e] = paa_s * B[e];
-    commit9<STAGE>(k, VA, P, cur, acc, S, cs, dt6);
-
-    // ---- vg:  k = A P_tg (+ C P_cg, P_cg = P_theta,bg at step start)
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            double s = 0.0;
-#pragma unroll
-            for (int m = 0; m < 3; m++) s = fma(A[3 * i + m], tg[3 * m + j], s);
-            k[3 * i + j] = s;
-        }
-    if (MODEL == 2) {
-        double cg[9];
-        ld9(P, S, TG, cg);
+        double ct[9], cc[9];
+        ld9<S>(cur, CT, ct); ldsym<S>(P, TT, cc);
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
-            for (int j = 0; j < 3; j++)
+            for (int j = 0; j < 3; j++) {
+                double s = 0.0;
 #pragma unroll
-                for (int m = 0; m < 3; m++) k[3 * i + j] = fma(C[3 * i + m], cg[3 * m + j], k[3 * i + j]);
+                for (int m = 0; m < 3; m++) s = fma(ct[3 * i + m], A[3 * j + m], s);
+#pragma unroll
+                for (int m = 0; m < 3; m++) s = fma(cc[3 * i + m], C[3 * j + m], s);
+                SM(cur, CV + 3 * i + j) = fma(s, cs, SM(P, VT + 3 * j + i));
+            }
+        CPI_SECTION();
     }
-    commit9<STAGE>(k, VG, P, cur, acc, S, cs, dt6);
-
-    // ---- tt:  k = M + M^T + q_w I,  M = -W P_tt - P_tg^T     (-W x = x cross w, column-wise)
-    {
-        double M[9];
+    {   // ---- vtheta:  k = A P_tt + P_vtheta W - P_vg (+ C P_ctheta)
+        double vt[9], tt[9], vg[9];
+        ld9<S>(src, VT, vt); ldsym<S>(src, TT, tt); ld9<S>(src, VG, vg);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            double c3[3];
+            cross(&vt[3 * i], w, c3);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                double s = c3[j] - vg[3 * i + j];
+#pragma unroll
+                for (int m = 0; m < 3; m++) s = fma(A[3 * i + m], tt[3 * m + j], s);
+                k[3 * i + j] = s;
+            }
+        }
+        if (MODEL == 2) {
+            double ct[9];
+            ld9<S>(cur, CT, ct);
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+#pragma unroll
+                    for (int m = 0; m < 3; m++) k[3 * i + j] = fma(C[3 * i + m], ct[3 * m + j], k[3 * i + j]);
+            // ---- ctheta (transient):  k = P_ctheta W - P_cg ;  P_cg = P_theta,bg at step start (constant), base = P_tt
+            if (STAGE < 4) {
+                double cg[9], bt[9];
+                ld9<S>(P, TG, cg); ldsym<S>(P, TT, bt);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    double c3[3];
+                    cross(&ct[3 * i], w, c3);
+#pragma unroll
+                    for (int j = 0; j < 3; j++) SM(cur, CT + 3 * i + j) = fma(c3[j] - cg[3 * i + j], cs, bt[3 * i + j]);
+                }
+            }
+        }
+        commit9<STAGE, S>(k, VT, P, cur, acc, cs, dt6);
+    }
+    CPI_SECTION();
+    {   // ---- va:  k = paa * B
+#pragma unroll
+        for (int e = 0; e < 9; e++) k[e] = paa_s * B[e];
+        commit9<STAGE, S>(k, VA, P, cur, acc, cs, dt6);
+    }
+    CPI_SECTION();
+    {   // ---- vg:  k = A P_tg (+ C P_cg, P_cg = P_theta,bg at step start)
+        double tg[9];
+        ld9<S>(src, TG, tg);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                double s = 0.0;
+#pragma unroll
+                for (int m = 0; m < 3; m++) s = fma(A[3 * i + m], tg[3 * m + j], s);
+                k[3 * i + j] = s;
+            }
+        if (MODEL == 2) {
+            double cg[9];
+            ld9<S>(P, TG, cg);
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+#pragma unroll
+                    for (int m = 0; m < 3; m++) k[3 * i + j] = fma(C[3 * i + m], cg[3 * m + j], k[3 * i + j]);
+        }
+        commit9<STAGE, S>(k, VG, P, cur, acc, cs, dt6);
+    }
+    CPI_SECTION();
+    {   // ---- tt:  k = M + M^T + q_w I,  M = -W P_tt - P_tg^T     (-W x = x cross w, column-wise)
+        //      tg:  k = -W P_tg - pgg I
+        double tt[9], tg[9], M[9];
+        ldsym<S>(src, TT, tt); ld9<S>(src, TG, tg);
 #pragma unroll
         for (int j = 0; j < 3; j++) {
             double col[3] = {tt[j], tt[3 + j], tt[6 + j]}, c3[3];
@@ -282,17 +318,17 @@ CPI_DEV void rk4_stage(double* P, double* cur, double* acc, int S, const double*
         for (int i = 0; i < 3; i++)
 #pragma unroll
             for (int j = i; j < 3; j++)
-                commit<STAGE>(M[3 * i + j] + M[3 * j + i] + (i == j ? q_w : 0.0), TT + sym3(i, j), P, cur, acc, S, cs, dt6);
-    }
-    // ---- tg:  k = -W P_tg - pgg I
+                commit<STAGE, S>(M[3 * i + j] + M[3 * j + i] + (i == j ? q_w : 0.0), TT + sym3(i, j), P, cur, acc, cs, dt6);
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        double col[3] = {tg[j], tg[3 + j], tg[6 + j]}, c3[3];
-        cross(col, w, c3);
+        for (int j = 0; j < 3; j++) {
+            double col[3] = {tg[j], tg[3 + j], tg[6 + j]}, c3[3];
+            cross(col, w, c3);
 #pragma unroll
-        for (int i = 0; i < 3; i++) k[3 * i + j] = c3[i] - (i == j ? pgg_s : 0.0);
+            for (int i = 0; i < 3; i++) k[3 * i + j] = c3[i] - (i == j ? pgg_s : 0.0);
+        }
+        commit9<STAGE, S>(k, TG, P, cur, acc, cs, dt6);
     }
-    commit9<STAGE>(k, TG, P, cur, acc, S, cs, dt6);
+    CPI_SECTION();
 }
 
 // rows of  -R^T [a x] : row i = a cross r_i  with r_i = column i of R (R row-major)
@@ -321,39 +357,27 @@ CPI_DEV void rot_apply(double a, double b, const double* w, const double* R, dou
     mul33(D, R, out);
 }
 
-struct Coef { double f1, f2, f3, f4, d1, d2, d3, d4; };
-// CpiV1.h:132-142, 196-238 (== CpiV2.h:158-168, 231-274)
-CPI_DEV void coefficients(bool small_w, double dt, double mag, double th, double s, double c, Coef& k) {
-    const double dt2 = dt * dt, dt3 = dt2 * dt;
-    if (small_w) {
-        k.f1 = -(dt3 / 3.0); k.f2 = (dt2 * dt2) / 8.0; k.f3 = -(dt2 / 2.0); k.f4 = dt3 / 6.0;
-        k.d1 = -(dt3 * dt2 / 15.0); k.d2 = (dt3 * dt3) / 72.0; k.d3 = -(dt2 * dt2 / 12.0); k.d4 = (dt3 * dt2) / 60.0;
-    } else {
-        const double m2 = mag * mag, m3 = m2 * mag, m4 = m2 * m2, th2 = th * th;
-        k.f1 = (th * c - s) / m3;
-        k.f2 = (th2 - 2.0 * c - 2.0 * th * s + 2.0) / (2.0 * m4);
-        k.f3 = -(1.0 - c) / m2;
-        k.f4 = (th - s) / m3;
-        k.d1 = (th2 * s - 3.0 * s + 3.0 * th * c) / (m4 * mag);
-        k.d2 = (th2 - 4.0 * c - 4.0 * th * s + th2 * c + 4.0) / (m4 * m2);
-        k.d3 = (2.0 * (c - 1.0) + th * s) / m4;
-        k.d4 = (2.0 * th + th * c - 3.0 * s) / (m4 * mag);
-    }
-}
-
 // =====================================================================================================================
+// Sample stream: per-window contiguous entries of 7 doubles.  Default mode stages it with 1-D TMA bulk copies
+// (cp.async.bulk -> SASS UBLKCP): every lane owns two 128-byte line buffers and two mbarriers and keeps two chunks of
+// two samples (112 B, fetched as ONE aligned 128-byte transaction that also covers the 8-byte misalignment of odd
+// window offsets) in flight ahead of the arithmetic.  The last chunk of a window is read with plain loads because the
+// aligned 128-byte fetch could run past the end of the caller's buffer there.
 template <int MODEL, bool AVG, bool ANALYTIC>
-__global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
-    extern __shared__ double smem[];
-    const int S = p.wpb;
+__global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
+    using T = Tile<MODEL>;
+    constexpr int S = T::S;
+    extern __shared__ __align__(128) double smem[];
     const int tid = threadIdx.x;
-    const int64_t win = (int64_t)blockIdx.x * S + tid;
-    if (tid >= S || win >= p.n_windows) return;
+    const int64_t win = (int64_t)blockIdx.x * p.wpb + tid;
+    if (tid >= p.wpb || win >= p.n_windows) return;
 
     double* P = smem + tid;
-    double* acc = P + (size_t)NP * S;
-    double* cur = acc + (size_t)NP * S;
-    double* Dj = cur + (size_t)(MODEL == 2 ? NCUR2 : NP) * S;   // model 2 only
+    double* acc = P + (size_t)T::OFF_ACC * S;
+    double* cur = P + (size_t)T::OFF_CUR * S;
+    double* Jt = P + (size_t)T::OFF_J * S;                       // analytic Jacobians, or Discrete_J_b blocks (model 2 default)
+    double* buf = smem + (size_t)T::ELEMS * S + (size_t)tid * (2 * BUF_DOUBLES);
+    const uint32_t bar0 = smem_u32(smem + (size_t)(T::ELEMS + 2 * BUF_DOUBLES) * S + 2 * tid);
 
     // ---- per-window constants (setLinearizationPoints, CpiBase.h:73-80)
     const double* lin = p.lin + win * CPI_LIN_DOUBLES;
@@ -371,35 +395,53 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
     if (nsteps < 0) nsteps = 0;
     const double* sp = p.samples + o0 * CPI_SAMPLE_DOUBLES;
 
+    // ---- TMA pipeline set-up
+    const int shift = (int)(o0 & 1);                     // 56*o0 bytes is 16-byte aligned iff o0 is even
+    const int64_t n_tma = AVG ? 0 : (nsteps > 0 ? (nsteps - 1) / 2 : 0);   // chunks with at least one more sample after them
+    if (!AVG) {
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+            if (c < n_tma) {
+                mbar_arrive_expect_tx(bar0 + 8 * c, 128);
+                bulk_g2s(smem_u32(buf + c * BUF_DOUBLES), sp + 14 * c - shift, 128, bar0 + 8 * c);
+            }
+    }
+
     // ---- state (CpiBase.h:99-124 initialisers)
     double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     double alpha[3] = {0, 0, 0}, beta[3] = {0, 0, 0}, DT = 0.0;
-    double Jq[9], Ja[9], Jb[9], Ha[9], Hb[9], Oa[9], Ob[9];
-#pragma unroll
-    for (int e = 0; e < 9; e++) { Jq[e] = Ja[e] = Jb[e] = Ha[e] = Hb[e] = Oa[e] = Ob[e] = 0.0; }
     double pgg = 0.0, paa = 0.0;
 #pragma unroll 1
     for (int e = 0; e < NP; e++) SM(P, e) = 0.0;
-    if (MODEL == 2) {
 #pragma unroll 1
-        for (int e = 0; e < ND; e++) SM(Dj, e) = 0.0;
-    }
-
-    // software prefetch of the next entry
-    double nx[7];
-    if (nsteps > 0 || AVG) {
-#pragma unroll
-        for (int e = 0; e < 7; e++) nx[e] = (nsteps > 0 || AVG) ? __ldg(sp + e) : 0.0;
-    }
+    for (int e = 0; e < T::NJ; e++) SM(Jt, e) = 0.0;
 
 #pragma unroll 1
     for (int64_t it = 0; it < nsteps; it++) {
-        double s0[7];
+        // ---- fetch entry `it` (and, for imu_avg, the (w, a) of entry it+1)
+        double s0[7], nx[6];
+        if (!AVG && it < 2 * n_tma) {
+            const int64_t c = it >> 1;
+            const int b = (int)(c & 1), j = (int)(it & 1);
+            if (j == 0) mbar_wait(bar0 + 8 * b, (uint32_t)((c >> 1) & 1));
+            const double* src = buf + b * BUF_DOUBLES + shift + 7 * j;
 #pragma unroll
-        for (int e = 0; e < 7; e++) s0[e] = nx[e];
-        if (it + 1 < nsteps + (AVG ? 1 : 0)) {
+            for (int e = 0; e < 7; e++) s0[e] = src[e];
+            if (j == 1 && c + 2 < n_tma) {
+                fence_proxy_async();                     // generic-proxy reads of this buffer are done; hand it to the async proxy
+                mbar_arrive_expect_tx(bar0 + 8 * b, 128);
+                bulk_g2s(smem_u32(buf + b * BUF_DOUBLES), sp + 14 * (c + 2) - shift, 128, bar0 + 8 * b);
+            }
+        } else {
 #pragma unroll
-            for (int e = 0; e < 7; e++) nx[e] = __ldg(sp + (it + 1) * CPI_SAMPLE_DOUBLES + e);
+            for (int e = 0; e < 7; e++) s0[e] = __ldg(sp + it * CPI_SAMPLE_DOUBLES + e);
+            if (AVG) {
+#pragma unroll
+                for (int e = 0; e < 6; e++) nx[e] = __ldg(sp + (it + 1) * CPI_SAMPLE_DOUBLES + e);
+            }
         }
         const double dt = s0[6];
         DT += dt;                                        // CpiV1.h:69
@@ -425,18 +467,20 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
         const double mag = sqrt(mag2);
         const double th = mag * dt;
         const bool small_w = mag < 0.008726646;          // CpiV1.h:101
-        double sn, cs_;
+        double sn, cs_, sh, ch;
         sincos(th, &sn, &cs_);
-        double sh, ch;
         sincos(mag * 0.5 * dt, &sh, &ch);
+        // one reciprocal instead of ~16 divisions (each an ~40-instruction subroutine); never used when small_w
+        const double im = small_w ? 0.0 : 1.0 / mag;
+        const double im2 = im * im;
 
         // ---- relative rotation, new and mid rotation (CpiV1.h:119-124, 267-269)
+        const double a1 = small_w ? dt : sn * im, b1 = small_w ? (dt * dt) * 0.5 : (1.0 - cs_) * im2;
         double R1[9], Rm[9];
+        rot_apply(a1, b1, wh, R, R1);
         {
-            const double a1 = small_w ? dt : sn / mag, b1 = small_w ? (dt * dt) / 2.0 : (1.0 - cs_) / (mag * mag);
-            rot_apply(a1, b1, wh, R, R1);
             const double hd = 0.5 * dt;
-            const double a2 = small_w ? hd : sh / mag, b2 = small_w ? (hd * hd) / 2.0 : (1.0 - ch) / (mag * mag);
+            const double a2 = small_w ? hd : sh * im, b2 = small_w ? (hd * hd) * 0.5 : (1.0 - ch) * im2;
             rot_apply(a2, b2, wh, R, Rm);
         }
         if (MODEL == 2 && AVG) {                         // CpiV2.h:146-149: average the LOCAL acceleration with the NEW rotation
@@ -446,8 +490,27 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
             for (int e = 0; e < 3; e++) { ah[e] += nx[3 + e] - ba[e] - g1[e]; ah[e] = 0.5 * ah[e]; }
         }
 
-        Coef kf;
-        coefficients(small_w, dt, mag, th, sn, cs_, kf);
+        // ---- closed-form coefficients (CpiV1.h:132-142, 196-238 == CpiV2.h:158-168, 231-274)
+        double f1, f2, f3, f4, d1, d2, d3, d4;
+        {
+            const double dt2 = dt * dt, dt3 = dt2 * dt;
+            if (small_w) {
+                f1 = -(dt3 / 3.0); f2 = (dt2 * dt2) / 8.0; f3 = -(dt2 / 2.0); f4 = dt3 / 6.0;
+                d1 = -(dt3 * dt2 / 15.0); d2 = (dt3 * dt3) / 72.0; d3 = -(dt2 * dt2 / 12.0); d4 = (dt3 * dt2) / 60.0;
+            } else {
+                const double im3 = im2 * im, im4 = im2 * im2, th2 = th * th;
+                f1 = (th * cs_ - sn) * im3;
+                f2 = (th2 - 2.0 * cs_ - 2.0 * th * sn + 2.0) * (0.5 * im4);
+                f3 = -(1.0 - cs_) * im2;
+                f4 = (th - sn) * im3;
+                if (MODEL == 1 || ANALYTIC) {
+                    d1 = (th2 * sn - 3.0 * sn + 3.0 * th * cs_) * (im4 * im);
+                    d2 = (th2 - 4.0 * cs_ - 4.0 * th * sn + th2 * cs_ + 4.0) * (im4 * im2);
+                    d3 = (2.0 * (cs_ - 1.0) + th * sn) * im4;
+                    d4 = (2.0 * th + th * cs_ - 3.0 * sn) * (im4 * im);
+                }
+            }
+        }
 
         // W and W^2 entries
         const double W2[9] = {-(wh[1] * wh[1] + wh[2] * wh[2]), wh[0] * wh[1], wh[0] * wh[2],
@@ -456,11 +519,11 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
         const double Wm[9] = {0.0, -wh[2], wh[1], wh[2], 0.0, -wh[0], -wh[1], wh[0], 0.0};
         double aarg[9], barg[9], Hal[9], Hbe[9];
         {
-            const double hdt2 = (dt * dt) / 2.0;
+            const double hdt2 = (dt * dt) * 0.5;
 #pragma unroll
             for (int e = 0; e < 9; e++) {
-                aarg[e] = ((e % 4 == 0) ? hdt2 : 0.0) + kf.f1 * Wm[e] + kf.f2 * W2[e];     // CpiV1.h:145
-                barg[e] = ((e % 4 == 0) ? dt : 0.0) + kf.f3 * Wm[e] + kf.f4 * W2[e];       // CpiV1.h:146
+                aarg[e] = ((e % 4 == 0) ? hdt2 : 0.0) + f1 * Wm[e] + f2 * W2[e];     // CpiV1.h:145
+                barg[e] = ((e % 4 == 0) ? dt : 0.0) + f3 * Wm[e] + f4 * W2[e];       // CpiV1.h:146
             }
         }
         mulT33(R1, aarg, Hal);                            // R_tau12k * alpha_arg
@@ -476,33 +539,42 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
         }
 
         if (MODEL == 1 || ANALYTIC) {
-            // ---- analytic bias Jacobians (CpiV1.h:162-259; CpiV2.h:188-305)
-            double Jsave[9];
+            // ---- analytic bias Jacobians (CpiV1.h:162-259; CpiV2.h:188-305); state lives in the tile, not in registers
+            double Jq[9], Jsave[9];
+            ld9<S>(Jt, J_Q, Jq);
 #pragma unroll
             for (int e = 0; e < 9; e++) Jsave[e] = Jq[e];
             {
-                const double c1 = small_w ? 0.5 : (1.0 - cs_) / (th * th), c2 = small_w ? (1.0 / 6.0) : (th - sn) / (th * th * th);
-                const double a1 = small_w ? dt : sn / mag, b1 = small_w ? (dt * dt) / 2.0 : (1.0 - cs_) / (mag * mag);
+                const double ith = small_w ? 0.0 : 1.0 / th;
+                const double c1 = small_w ? 0.5 : (1.0 - cs_) * (ith * ith), c2 = small_w ? (1.0 / 6.0) : (th - sn) * (ith * ith * ith);
                 double t9[9];
-                rot_apply(a1, b1, wh, Jq, t9);            // R_tau2tau1 * J_q
+                rot_apply(a1, b1, wh, Jsave, t9);         // R_tau2tau1 * J_q
                 const double ca = c1 * dt, cb = c2 * dt * dt;   // w_tx = dt*W, w_tx^2 = dt^2 W2
 #pragma unroll
-                for (int e = 0; e < 9; e++) Jq[e] = t9[e] + (((e % 4 == 0) ? 1.0 : 0.0) - ca * Wm[e] + cb * W2[e]) * dt;   // CpiV1.h:167
+                for (int e = 0; e < 9; e++) {
+                    Jq[e] = t9[e] + (((e % 4 == 0) ? 1.0 : 0.0) - ca * Wm[e] + cb * W2[e]) * dt;   // CpiV1.h:167
+                    SM(Jt, J_Q + e) = Jq[e];
+                }
             }
 #pragma unroll
-            for (int e = 0; e < 9; e++) { Ha[e] -= Hal[e]; Ha[e] += dt * Hb[e]; Hb[e] -= Hbe[e]; }   // CpiV1.h:170-172 (old H_b)
+            for (int e = 0; e < 9; e++) {                  // CpiV1.h:170-172 (old H_b)
+                const double hb = SM(Jt, H_B + e);
+                SM(Jt, H_A + e) = (SM(Jt, H_A + e) - Hal[e]) + dt * hb;
+                SM(Jt, H_B + e) = hb - Hbe[e];
+            }
             if (MODEL == 2) {                              // CpiV2.h:203-205
-                double sk[9] = {0.0, -g_k[2], g_k[1], g_k[2], 0.0, -g_k[0], -g_k[1], g_k[0], 0.0}, t1[9], t2[9];
+                const double sk[9] = {0.0, -g_k[2], g_k[1], g_k[2], 0.0, -g_k[0], -g_k[1], g_k[0], 0.0};
+                double t1[9], t2[9], t4[9];
                 mul33(R, sk, t1);
                 mul33(Hal, t1, t2);
+                mul33(Hbe, t1, t4);
 #pragma unroll
-                for (int e = 0; e < 9; e++) { Oa[e] += dt * Ob[e]; Oa[e] += -t2[e]; }
-                mul33(Hbe, t1, t2);
-#pragma unroll
-                for (int e = 0; e < 9; e++) Ob[e] += -t2[e];
+                for (int e = 0; e < 9; e++) {
+                    const double ob = SM(Jt, O_B + e);
+                    SM(Jt, O_A + e) = (SM(Jt, O_A + e) + dt * ob) + -t2[e];
+                    SM(Jt, O_B + e) = ob + -t4[e];
+                }
             }
-#pragma unroll
-            for (int e = 0; e < 9; e++) Ja[e] += Jb[e] * dt;   // CpiV1.h:241 (old J_b)
             // vectors shared by the three columns
             double ua[3], ub[3], Wa[3], W2a[3];
             mv33(aarg, ah, ua); mv33(barg, ah, ub);
@@ -512,7 +584,7 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
             for (int col = 0; col < 3; col++) {
                 const double e3[3] = {col == 0 ? 1.0 : 0.0, col == 1 ? 1.0 : 0.0, col == 2 ? 1.0 : 0.0};
                 const double jc[3] = {Jq[col], Jq[3 + col], Jq[6 + col]};   // NEW J_q e_i
-                double exa[3], exWa[3], Wexa[3], c1v[3], c2v[3], va_[3], vb_[3], o3[3];
+                double exa[3], exWa[3], Wexa[3], c1v[3], c2v[3], va_[3], vb_[3], oa3[3], ob3[3];
                 cross(e3, ah, exa);                        // e_ix a
                 cross(e3, Wa, exWa);                       // e_ix W a
                 cross(wh, exa, Wexa);                      // W e_ix a
@@ -521,33 +593,32 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
                 const double wi = wh[col];
 #pragma unroll
                 for (int e = 0; e < 3; e++) {
-                    va_[e] = -c1v[e] + (wi * kf.d1) * Wa[e] - kf.f1 * exa[e] + (wi * kf.d2) * W2a[e] - kf.f2 * (exWa[e] + Wexa[e]);
-                    vb_[e] = -c2v[e] + (wi * kf.d3) * Wa[e] - kf.f3 * exa[e] + (wi * kf.d4) * W2a[e] - kf.f4 * (exWa[e] + Wexa[e]);
+                    va_[e] = -c1v[e] + (wi * d1) * Wa[e] - f1 * exa[e] + (wi * d2) * W2a[e] - f2 * (exWa[e] + Wexa[e]);
+                    vb_[e] = -c2v[e] + (wi * d3) * Wa[e] - f3 * exa[e] + (wi * d4) * W2a[e] - f4 * (exWa[e] + Wexa[e]);
                 }
-                mvT33(R1, va_, o3);
-                if (MODEL == 2) {                          // - H_al [J_save e_i x] g_tau   (CpiV2.h:285-293)
-                    const double js[3] = {Jsave[col], Jsave[3 + col], Jsave[6 + col]};
+                mvT33(R1, va_, oa3);
+                mvT33(R1, vb_, ob3);
+                if (MODEL == 2) {                          // - H_al [J_save e_i x] g_tau (CpiV2.h:285-293); J_b column 0 carries
+                    const double js[3] = {Jsave[col], Jsave[3 + col], Jsave[6 + col]};   // the reference's "- -" = plus (:296-297)
                     double cg[3], u[3];
                     cross(js, g_tau, cg);
                     mv33(Hal, cg, u);
-                    o3[0] -= u[0]; o3[1] -= u[1]; o3[2] -= u[2];
-                }
-                Ja[col] += o3[0]; Ja[3 + col] += o3[1]; Ja[6 + col] += o3[2];
-                mvT33(R1, vb_, o3);
-                if (MODEL == 2) {                          // CpiV2.h:296-305; column 0 carries the reference's "- -" (plus) sign
-                    const double js[3] = {Jsave[col], Jsave[3 + col], Jsave[6 + col]};
-                    double cg[3], u[3];
-                    cross(js, g_tau, cg);
+                    oa3[0] -= u[0]; oa3[1] -= u[1]; oa3[2] -= u[2];
                     mv33(Hbe, cg, u);
-                    if (col == 0) { o3[0] += u[0]; o3[1] += u[1]; o3[2] += u[2]; }
-                    else { o3[0] -= u[0]; o3[1] -= u[1]; o3[2] -= u[2]; }
+                    if (col == 0) { ob3[0] += u[0]; ob3[1] += u[1]; ob3[2] += u[2]; }
+                    else { ob3[0] -= u[0]; ob3[1] -= u[1]; ob3[2] -= u[2]; }
                 }
-                Jb[col] += o3[0]; Jb[3 + col] += o3[1]; Jb[6 + col] += o3[2];
+#pragma unroll
+                for (int r = 0; r < 3; r++) {              // J_a += J_b*dt (old J_b, CpiV1.h:241) then the column terms
+                    const double jb = SM(Jt, J_B + 3 * r + col);
+                    SM(Jt, J_A + 3 * r + col) = (SM(Jt, J_A + 3 * r + col) + jb * dt) + oa3[r];
+                    SM(Jt, J_B + 3 * r + col) = jb + ob3[r];
+                }
             }
         }
 
         // ---- covariance: 4 RK4 stages on the block-sparse Lyapunov operator (CpiV1.h:272-353; CpiV2.h:326-422)
-        const double hdt = dt / 2.0, dt6 = dt / 6.0;
+        const double hdt = dt * 0.5, dt6 = dt / 6.0;
         double A[9], B[9], C[9];
         if (MODEL == 2) {
             // clone rows start as copies of the theta rows (B_k of the previous step, CpiV2.h:436-441)
@@ -562,13 +633,13 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
         }
         make_A(R, ah, A); make_B(R, B);
         if (MODEL == 2) make_A(R, g_tau, C);
-        rk4_stage<1, MODEL>(P, cur, acc, S, wh, A, B, C, pgg, paa, hdt, dt6, p.q_w, p.q_a);
+        rk4_stage<1, MODEL, S>(P, cur, acc, wh, A, B, C, pgg, paa, hdt, dt6, p.q_w, p.q_a);
         make_A(Rm, ah, A); make_B(Rm, B);
         if (MODEL == 2) make_A(Rm, g_tau, C);
         {
             const double pgg2 = fma(p.q_wb, hdt, pgg), paa2 = fma(p.q_ab, hdt, paa);
-            rk4_stage<2, MODEL>(P, cur, acc, S, wh, A, B, C, pgg2, paa2, hdt, dt6, p.q_w, p.q_a);
-            rk4_stage<3, MODEL>(P, cur, acc, S, wh, A, B, C, pgg2, paa2, dt, dt6, p.q_w, p.q_a);
+            rk4_stage<2, MODEL, S>(P, cur, acc, wh, A, B, C, pgg2, paa2, hdt, dt6, p.q_w, p.q_a);
+            rk4_stage<3, MODEL, S>(P, cur, acc, wh, A, B, C, pgg2, paa2, dt, dt6, p.q_w, p.q_a);
         }
         double A1[9], C1[9];
         if (MODEL == 2 && !ANALYTIC) {
@@ -579,7 +650,7 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
         if (MODEL == 2) make_A(R1, g_tau, C);
         {
             const double pgg4 = fma(p.q_wb, dt, pgg), paa4 = fma(p.q_ab, dt, paa);
-            rk4_stage<4, MODEL>(P, cur, acc, S, wh, A, B, C, pgg4, paa4, dt, dt6, p.q_w, p.q_a);
+            rk4_stage<4, MODEL, S>(P, cur, acc, wh, A, B, C, pgg4, paa4, dt, dt6, p.q_w, p.q_a);
         }
         pgg += dt6 * (p.q_wb + 2.0 * p.q_wb + 2.0 * p.q_wb + p.q_wb);
         paa += dt6 * (p.q_ab + 2.0 * p.q_ab + 2.0 * p.q_ab + p.q_ab);
@@ -590,7 +661,6 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
             // Row theta:  X' = -W X (- I for the bg column).   Row v: sum_s A_s X_theta,s + B_s/C_s/L_s.   Row p: integral of row v.
             double A0[9], C0[9];
             make_A(R, ah, A0); make_A(R, g_tau, C0);
-            // theta-theta and theta-bg columns of Phi, with stage values
             double Xtt[4][9], Xtg[4][9];   // stage VALUES Phi_s (s = 1..4) of the two theta-row blocks
             double ktt[4][9], ktg[4][9];   // stage DERIVATIVES
 #pragma unroll
@@ -621,18 +691,16 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
                 Ptt[e] = ((e % 4 == 0) ? 1.0 : 0.0) + dt6 * (ktt[0][e] + 2.0 * ktt[1][e] + 2.0 * ktt[2][e] + ktt[3][e]);
                 Ptg[e] = dt6 * (ktg[0][e] + 2.0 * ktg[1][e] + 2.0 * ktg[2][e] + ktg[3][e]);
             }
-            // v-row derivative blocks per stage: kv_X,s = A_s Phi_thetaX,s (+ direct block for the identity rows)
             const double* As[4] = {A0, A1, A1, A};
             const double* Cs[4] = {C0, C1, C1, C};
             double B0[9], Bm[9];
             make_B(R, B0); make_B(Rm, Bm);
             const double* Bs[4] = {B0, Bm, Bm, B};
-            // L_s = -R_s^T R_old [g_k x]  (CpiV2.h:336)
-            double L[4][9];
+            double L[4][9];                                 // L_s = -R_s^T R_old [g_k x]  (CpiV2.h:336)
             {
-                double sk[9] = {0.0, -g_k[2], g_k[1], g_k[2], 0.0, -g_k[0], -g_k[1], g_k[0], 0.0}, RS[9];
+                const double sk[9] = {0.0, -g_k[2], g_k[1], g_k[2], 0.0, -g_k[0], -g_k[1], g_k[0], 0.0};
+                double RS[9], t9[9];
                 mul33(R, sk, RS);
-                double t9[9];
                 mulT33(R, RS, t9);
 #pragma unroll
                 for (int e = 0; e < 9; e++) L[0][e] = -t9[e];
@@ -665,23 +733,21 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
             const double Ppv = dt6 * (1.0 + 2.0 + 2.0 + 1.0);   // Phi_p,v = that * I
             // apply: D' = B_k Phi D on columns {bg, ba, theta_klin}; D_c,X == D_theta,X (clone of the previous step)
             double Dtg[9], Dvg[9], Dpg[9], Dva[9], Dpa[9], Dvl[9], Dpl[9], n1[9], n2[9], n3[9];
-            ld9(Dj, S, D_TG, Dtg); ld9(Dj, S, D_VG, Dvg); ld9(Dj, S, D_PG, Dpg);
-            ld9(Dj, S, D_VA, Dva); ld9(Dj, S, D_PA, Dpa); ld9(Dj, S, D_VL, Dvl); ld9(Dj, S, D_PL, Dpl);
+            ld9<S>(Jt, D_TG, Dtg); ld9<S>(Jt, D_VG, Dvg); ld9<S>(Jt, D_PG, Dpg);
+            ld9<S>(Jt, D_VA, Dva); ld9<S>(Jt, D_PA, Dpa); ld9<S>(Jt, D_VL, Dvl); ld9<S>(Jt, D_PL, Dpl);
             double Pvtc[9], Pptc[9];
 #pragma unroll
             for (int e = 0; e < 9; e++) { Pvtc[e] = Pvt[e] + Pvc[e]; Pptc[e] = Ppt[e] + Ppc[e]; }
             mul33(Ptt, Dtg, n1); mul33(Pvtc, Dtg, n2); mul33(Pptc, Dtg, n3);
 #pragma unroll
             for (int e = 0; e < 9; e++) {
-                const double dpg = n3[e] + Ppg[e] + Ppv * Dvg[e] + Dpg[e];
-                const double dvg = n2[e] + Pvg[e] + Dvg[e];
-                const double dtg = n1[e] + Ptg[e];
-                const double dpa = Ppa[e] + Ppv * Dva[e] + Dpa[e];
-                const double dva = Pva[e] + Dva[e];
-                const double dpl = Ppl[e] + Ppv * Dvl[e] + Dpl[e];
-                const double dvl = Pvl[e] + Dvl[e];
-                SM(Dj, D_TG + e) = dtg; SM(Dj, D_VG + e) = dvg; SM(Dj, D_PG + e) = dpg;
-                SM(Dj, D_VA + e) = dva; SM(Dj, D_PA + e) = dpa; SM(Dj, D_VL + e) = dvl; SM(Dj, D_PL + e) = dpl;
+                SM(Jt, D_PG + e) = n3[e] + Ppg[e] + Ppv * Dvg[e] + Dpg[e];
+                SM(Jt, D_VG + e) = n2[e] + Pvg[e] + Dvg[e];
+                SM(Jt, D_TG + e) = n1[e] + Ptg[e];
+                SM(Jt, D_PA + e) = Ppa[e] + Ppv * Dva[e] + Dpa[e];
+                SM(Jt, D_VA + e) = Pva[e] + Dva[e];
+                SM(Jt, D_PL + e) = Ppl[e] + Ppv * Dvl[e] + Dpl[e];
+                SM(Jt, D_VL + e) = Pvl[e] + Dvl[e];
             }
         }
 
@@ -698,25 +764,25 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
         rot_2_quat(R, q);                                  // CpiV1.h:358 (only the last one is ever consumed)
         rec[CPI_REC_Q] = q[0]; rec[CPI_REC_Q + 1] = q[1]; rec[CPI_REC_Q + 2] = q[2]; rec[CPI_REC_Q + 3] = q[3];
     }
-    if (MODEL == 2 && !ANALYTIC) {                         // CpiV2.h:450-458
-        double t[9];
-        ld9(Dj, S, D_TG, t);
+    {
+        // Jacobian blocks: analytic state, or the read-out of Discrete_J_b (CpiV2.h:450-458: J_q = -D[theta,bg], J_a = D[p,bg],
+        // J_b = D[v,bg], H_a = D[p,ba], H_b = D[v,ba], O_a = D[p,l], O_b = D[v,l])
+        constexpr bool DJ = (MODEL == 2 && !ANALYTIC);
+        constexpr int oJq = DJ ? D_TG : J_Q, oJa = DJ ? D_PG : J_A, oJb = DJ ? D_VG : J_B, oHa = DJ ? D_PA : H_A, oHb = DJ ? D_VA : H_B,
+                      oOa = DJ ? D_PL : O_A, oOb = DJ ? D_VL : O_B;
 #pragma unroll
-        for (int e = 0; e < 9; e++) Jq[e] = -t[e];
-        ld9(Dj, S, D_PG, Ja); ld9(Dj, S, D_VG, Jb); ld9(Dj, S, D_PA, Ha); ld9(Dj, S, D_VA, Hb); ld9(Dj, S, D_PL, Oa); ld9(Dj, S, D_VL, Ob);
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                rec[CPI_REC_R + i + 3 * j] = R[3 * i + j];
+                rec[CPI_REC_JQ + i + 3 * j] = DJ ? -SM(Jt, oJq + 3 * i + j) : SM(Jt, oJq + 3 * i + j);
+                rec[CPI_REC_JA + i + 3 * j] = SM(Jt, oJa + 3 * i + j);
+                rec[CPI_REC_JB + i + 3 * j] = SM(Jt, oJb + 3 * i + j);
+                rec[CPI_REC_HA + i + 3 * j] = SM(Jt, oHa + 3 * i + j);
+                rec[CPI_REC_HB + i + 3 * j] = SM(Jt, oHb + 3 * i + j);
+                if (MODEL == 2) { rec[CPI_REC_OA + i + 3 * j] = SM(Jt, oOa + 3 * i + j); rec[CPI_REC_OB + i + 3 * j] = SM(Jt, oOb + 3 * i + j); }
+            }
     }
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            rec[CPI_REC_R + i + 3 * j] = R[3 * i + j];
-            rec[CPI_REC_JQ + i + 3 * j] = Jq[3 * i + j];
-            rec[CPI_REC_JA + i + 3 * j] = Ja[3 * i + j];
-            rec[CPI_REC_JB + i + 3 * j] = Jb[3 * i + j];
-            rec[CPI_REC_HA + i + 3 * j] = Ha[3 * i + j];
-            rec[CPI_REC_HB + i + 3 * j] = Hb[3 * i + j];
-            if (MODEL == 2) { rec[CPI_REC_OA + i + 3 * j] = Oa[3 * i + j]; rec[CPI_REC_OB + i + 3 * j] = Ob[3 * i + j]; }
-        }
 #pragma unroll
     for (int e = 0; e < 3; e++) { rec[CPI_REC_ALPHA + e] = alpha[e]; rec[CPI_REC_BETA + e] = beta[e]; }
     rec[CPI_REC_DT] = DT;
@@ -745,39 +811,43 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
 
 // ---- host-side launcher (called from capi.cu) --------------------------------------------------------------------------
 template <int MODEL, bool AVG, bool ANALYTIC>
-static cudaError_t launch_one(const PreintParams& p, int grid, int block, size_t smem, cudaStream_t st) {
+static cudaError_t launch_one(const PreintParams& p, int grid, int block, cudaStream_t st) {
     auto kern = k_preintegrate<MODEL, AVG, ANALYTIC>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, block, smem, st>>>(p);
+    static bool configured = false;     // per instantiation; the attribute is sticky per device context
+    static int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured || configured_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes<MODEL>());
+        if (e != cudaSuccess) return e;
+        configured = true; configured_dev = dev;
+    }
+    kern<<<grid, block, tile_bytes<MODEL>(), st>>>(p);
     return cudaGetLastError();
 }
 
 // Windows per block.  Small batches: spread over all SMs in ONE wave (a second wave would double the latency of a
-// latency-bound launch).  Large batches: as many windows as the SM's shared memory holds, in whole warps.
+// latency-bound launch).  Large batches: the tile's compile-time capacity S.
 int preint_pick_wpb(int model, int64_t n_windows, int num_sms, int max_smem_bytes) {
-    const int per_win = tile_doubles(model) * 8;
-    int fit = max_smem_bytes / per_win;
-    if (fit > 128) fit = 128;
-    if (fit < 1) fit = 1;
+    (void)max_smem_bytes;
+    const int cap = model == 1 ? Tile<1>::S : Tile<2>::S;
     const int64_t need = (n_windows + num_sms - 1) / num_sms;
-    if (need <= fit) return (int)(need < 1 ? 1 : need);
-    return fit >= 32 ? fit / 32 * 32 : fit;
+    if (need <= cap) return (int)(need < 1 ? 1 : need);
+    return cap;
 }
 
 cudaError_t preint_launch(int model, int flags, const PreintParams& p0, int num_sms, int max_smem_bytes, cudaStream_t st, int* launches) {
     PreintParams p = p0;
     if (p.n_windows == 0) return cudaSuccess;
+    if ((size_t)max_smem_bytes < (model == 1 ? tile_bytes<1>() : tile_bytes<2>())) return cudaErrorInvalidConfiguration;
     p.wpb = preint_pick_wpb(model, p.n_windows, num_sms, max_smem_bytes);
     const int block = (p.wpb + 31) / 32 * 32;
-    const int64_t grid64 = (p.n_windows + p.wpb - 1) / p.wpb;
-    const size_t smem = (size_t)tile_doubles(model) * 8 * p.wpb;
-    const int grid = (int)grid64;
+    const int grid = (int)((p.n_windows + p.wpb - 1) / p.wpb);
     const bool avg = flags & CPI_FLAG_IMU_AVG, ana = flags & CPI_FLAG_ANALYTIC_JACOBIANS;
     cudaError_t e;
-    if (model == 1) e = avg ? launch_one<1, true, false>(p, grid, block, smem, st) : launch_one<1, false, false>(p, grid, block, smem, st);
-    else if (!ana) e = avg ? launch_one<2, true, false>(p, grid, block, smem, st) : launch_one<2, false, false>(p, grid, block, smem, st);
-    else e = avg ? launch_one<2, true, true>(p, grid, block, smem, st) : launch_one<2, false, true>(p, grid, block, smem, st);
+    if (model == 1) e = avg ? launch_one<1, true, false>(p, grid, block, st) : launch_one<1, false, false>(p, grid, block, st);
+    else if (!ana) e = avg ? launch_one<2, true, false>(p, grid, block, st) : launch_one<2, false, false>(p, grid, block, st);
+    else e = avg ? launch_one<2, true, true>(p, grid, block, st) : launch_one<2, false, true>(p, grid, block, st);
     if (launches) *launches = 1;
     return e;
 }
