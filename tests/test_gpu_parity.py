@@ -194,3 +194,15 @@ def test_full_size_properties(cuda, oracle):
     off = np.arange(len(sel) + 1, dtype=np.int64) * ns
     worst = compare_records(r[sel], ref, 1, in_band=window_band(S[sel].reshape(-1, 7), off, L[sel]))
     print({k: f"{v:.1e}" for k, v in worst.items()})
+
+
+def test_cpp_facade_against_reference_headers(cuda):
+    """include/cpi_b200/CpiGpu.h (CpiV1Gpu / CpiV2Gpu : CpiBase) vs the reference's own CpiV1 / CpiV2 compiled into the same
+    binary (tests/cpp/test_facade, prebuilt where /root/reference exists)."""
+    import os, subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "test_facade")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/test_facade not built (needs the reference headers at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "FACADE OK" in r.stdout
