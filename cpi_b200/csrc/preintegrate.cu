@@ -46,25 +46,32 @@ enum : int {
     D_TG = 0, D_VG = 9, D_PG = 18, D_VA = 27, D_PA = 36, D_VL = 45, D_PL = 54, ND = 63,
     // analytic Jacobian state (model 1; model 2 with CPI_FLAG_ANALYTIC_JACOBIANS): same 63-double region
     J_Q = 0, J_A = 9, J_B = 18, H_A = 27, H_B = 36, O_A = 45, O_B = 54,
-    // TMA staging: two buffers of one 128-byte line (+16 B pad against bank conflicts) per window, NOT element-major
-    BUF_DOUBLES = 18
+    // TMA staging: two buffers of one 128-byte line per window, NOT element-major
+    BUF_DOUBLES = 16
 };
 
 // Per-model tile description.  S (window stride == max windows per CTA) is a compile-time constant so that every
 // shared-memory access is [base + immediate]; it is chosen as large as 227 KB allow.
+//   [0, 90)    covariance tile, buffer a   } ping-pong: a sample reads the old tile and writes the new one, because a
+//   [90, 180)  covariance tile, buffer b   } block's old value is still the stage-1 input of blocks processed after it
+//   [180, ..)  RK4 stage-value slots (stage values 2..4 of the blocks that later blocks depend on; slots are re-used as
+//              soon as the last dependant has run -- see rk4_cascade)
+//   then       Jacobian state (45 / 63 doubles)
+enum : int { SLOT_A = 0, SLOT_B = 27, SLOT_C = 54, SLOT_D = 81 /*18*/, SLOT_E = 99 /*model 2*/ };
 template <int MODEL> struct Tile;
 template <> struct Tile<1> {
-    static constexpr int NCUR = NP, NJ = 45, S = 80;
-    static constexpr int OFF_ACC = NP, OFF_CUR = 2 * NP, OFF_J = 3 * NP, ELEMS = 3 * NP + NJ;     // 315 element-major doubles
+    static constexpr int NSLOT = 99, NJ = 45, S = 80;
+    static constexpr int OFF_PB = NP, OFF_SL = 2 * NP, OFF_J = 2 * NP + NSLOT, ELEMS = 2 * NP + NSLOT + NJ;   // 324
 };
 template <> struct Tile<2> {
-    static constexpr int NCUR = NCUR2, NJ = ND, S = 72;
-    static constexpr int OFF_ACC = NP, OFF_CUR = 2 * NP, OFF_J = 2 * NP + NCUR2, ELEMS = 2 * NP + NCUR2 + ND;   // 360
+    static constexpr int NSLOT = 126, NJ = ND, S = 72;
+    static constexpr int OFF_PB = NP, OFF_SL = 2 * NP, OFF_J = 2 * NP + NSLOT, ELEMS = 2 * NP + NSLOT + ND;   // 369
 };
 template <int MODEL> __host__ __device__ constexpr size_t tile_bytes() {
-    // element-major part + per-window staging buffers (2 x 18 doubles) + 2 mbarriers
+    // element-major part + per-window staging buffers (2 x 16 doubles = two 128-byte lines) + 2 mbarriers
     return (size_t)Tile<MODEL>::S * (Tile<MODEL>::ELEMS + 2 * BUF_DOUBLES + 2) * sizeof(double);
 }
+static_assert(tile_bytes<1>() <= 232448 && tile_bytes<2>() <= 232448, "tile exceeds 227 KB");
 
 // ---- TMA (1-D bulk copy) + mbarrier primitives: SASS UBLKCP / SYNCS ---------------------------------------------------
 CPI_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -96,240 +103,34 @@ template <int S> CPI_DEV void ldsym(const double* b, int off, double* x) {   // 
     x[0] = a0; x[1] = a1; x[2] = a2; x[3] = a1; x[4] = a3; x[5] = a4; x[6] = a2; x[7] = a4; x[8] = a5;
 }
 
-// RK4 bookkeeping for one entry.  Reference: P2 = P + k1*dt/2, P3 = P + k2*dt/2, P4 = P + k3*dt,
-// P += (dt/6)*(k1 + 2 k2 + 2 k3 + k4)   (CpiV1.h:312, 323, 344, 352).
-template <int STAGE, int S> CPI_DEV void commit(double k, int idx, double* P, double* cur, double* acc, double cs, double dt6) {
-    if (STAGE == 1) { SM(cur, idx) = fma(k, cs, SM(P, idx)); SM(acc, idx) = k; }
-    else if (STAGE < 4) { const double a = SM(acc, idx); SM(cur, idx) = fma(k, cs, SM(P, idx)); SM(acc, idx) = fma(2.0, k, a); }
-    else { SM(P, idx) = fma(dt6, SM(acc, idx) + k, SM(P, idx)); }
-}
-template <int STAGE, int S> CPI_DEV void commit9(const double* k, int off, double* P, double* cur, double* acc, double cs, double dt6) {
-#pragma unroll
-    for (int e = 0; e < 9; e++) commit<STAGE, S>(k[e], off + e, P, cur, acc, cs, dt6);
-}
-
-// One RK4 stage over the whole tile.  src = where this stage's P_s lives (P itself for stage 1, cur otherwise).
-// Blocks are visited in REVERSE dependency order so that cur can be updated in place; every section loads just the
-// blocks it needs (LDS with immediate offsets) and is fenced from its neighbours with a compiler barrier so that the
-// scheduler does not hoist a whole stage's loads to the top and spill (the tile is the spill space by design).
-//   w: w_hat;  A = -R*^T [a_hat x];  B = -R*^T;  C = -R*^T [g_tau x] (model 2);  pgg_s/paa_s: stage values of the scalar blocks.
+// =====================================================================================================================
+// Covariance: the reference's RK4 on  Pdot = F P + P F^T + G Qc G^T  (CpiV1.h:272-353; CpiV2.h:326-422), block-serial.
+//
+// F is block lower-triangular in the order (bg, ba | theta | v | p): theta-row blocks depend only on bg/theta blocks,
+// v-row blocks on theta/ba/v blocks, p-row blocks on v/p blocks.  RK4 on a triangular system can therefore be run ONE
+// 3x3 BLOCK AT A TIME -- all four stages of a block in registers, given the four stage values of the blocks it depends
+// on -- with exactly the arithmetic of the stage-by-stage form.  Compared with sweeping the whole tile once per stage
+// this removes the accumulator array and about half of the shared-memory traffic.  Order and slot reuse (model 1):
+//     tg->A  tt->B  vg->C(+pg)  vt->A  pt->B  va->C(+pa)  vv->D  pv->A  pp
+// model 2 adds the transient clone-row blocks ct (->A, before vt which then goes to E) and cv (->B, after vt); the p-row
+// transient cp is recomputed from cv's stage values, like pg from vg and pa from va.
+// Stage s (0..3) of a block lives in the OLD tile (s == 0) or in its slot at (s-1)*n.
 #define CPI_SECTION() asm volatile("" ::: "memory")
-template <int STAGE, int MODEL, int S>
-CPI_DEV void rk4_stage(double* P, double* cur, double* acc, const double* w, const double* A, const double* B, const double* C,
-                       double pgg_s, double paa_s, double cs, double dt6, double q_w, double q_a) {
-    const double* src = (STAGE == 1) ? P : cur;
-    double k[9];
+#define CN(s) ((s) < 2 ? hdt : dt)                       /* x_{s+2} = x_1 + CN(s) k_{s+1}:  dt/2, dt/2, dt   (CpiV1.h:312, 323, 344) */
+#define RS(s) ((s) == 0 ? R : ((s) == 3 ? R1 : Rm))       /* F evaluated at R_old, R_mid, R_mid, R_new */
+#define KSUM(ks, k, s) ((s) == 0 ? (k) : ((s) == 3 ? (ks) + (k) : fma(2.0, (k), (ks))))   /* ((k1 + 2 k2) + 2 k3) + k4  (CpiV1.h:352) */
 
-    {   // ---- pp:  k = P_pv + P_pv^T
-        double pv[9];
-        ld9<S>(src, PV, pv);
+template <int S> CPI_DEV void st9(double* b, int off, const double* x) {
 #pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = i; j < 3; j++) commit<STAGE, S>(pv[3 * i + j] + pv[3 * j + i], PP + sym3(i, j), P, cur, acc, cs, dt6);
-    }
-    CPI_SECTION();
-    {   // ---- pv:  k = P_vv + P_ptheta A^T + P_pa B^T (+ P_cp^T C^T)
-        double pt[9], pa[9], vv[9];
-        ld9<S>(src, PT, pt); ld9<S>(src, PA, pa); ldsym<S>(src, VV, vv);
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                double s = vv[3 * i + j];
-#pragma unroll
-                for (int m = 0; m < 3; m++) s = fma(pt[3 * i + m], A[3 * j + m], s);
-#pragma unroll
-                for (int m = 0; m < 3; m++) s = fma(pa[3 * i + m], B[3 * j + m], s);
-                k[3 * i + j] = s;
-            }
-        if (MODEL == 2) {
-            double cp[9];
-            ld9<S>(cur, CP, cp);
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int j = 0; j < 3; j++)
-#pragma unroll
-                    for (int m = 0; m < 3; m++) k[3 * i + j] = fma(cp[3 * m + i], C[3 * j + m], k[3 * i + j]);
-            // ---- cp (transient):  k = P_cv ; base value = P_theta,p = P_ptheta^T
-            if (STAGE < 4) {
-#pragma unroll
-                for (int i = 0; i < 3; i++)
-#pragma unroll
-                    for (int j = 0; j < 3; j++) SM(cur, CP + 3 * i + j) = fma(SM(cur, CV + 3 * i + j), cs, SM(P, PT + 3 * j + i));
-            }
-        }
-        commit9<STAGE, S>(k, PV, P, cur, acc, cs, dt6);
-    }
-    CPI_SECTION();
-    {   // ---- ptheta:  k = P_vtheta + P_ptheta W - P_pg
-        double pt[9], vt[9], pg[9];
-        ld9<S>(src, PT, pt); ld9<S>(src, VT, vt); ld9<S>(src, PG, pg);
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            double c3[3];
-            cross(&pt[3 * i], w, c3);
-#pragma unroll
-            for (int j = 0; j < 3; j++) k[3 * i + j] = vt[3 * i + j] + c3[j] - pg[3 * i + j];
-        }
-        commit9<STAGE, S>(k, PT, P, cur, acc, cs, dt6);
-    }
-    CPI_SECTION();
-    {   // ---- pa:  k = P_va        pg:  k = P_vg
-        double va[9];
-        ld9<S>(src, VA, va);
-        commit9<STAGE, S>(va, PA, P, cur, acc, cs, dt6);
-        ld9<S>(src, VG, va);
-        commit9<STAGE, S>(va, PG, P, cur, acc, cs, dt6);
-    }
-    CPI_SECTION();
-    {   // ---- vv:  k = M + M^T + q_a I,  M = A P_vtheta^T + B P_va^T (+ C P_cv)
-        double vt[9], va[9], M[9];
-        ld9<S>(src, VT, vt); ld9<S>(src, VA, va);
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                double s = 0.0;
-#pragma unroll
-                for (int m = 0; m < 3; m++) s = fma(A[3 * i + m], vt[3 * j + m], s);
-#pragma unroll
-                for (int m = 0; m < 3; m++) s = fma(B[3 * i + m], va[3 * j + m], s);
-                M[3 * i + j] = s;
-            }
-        if (MODEL == 2) {
-            double cv[9];
-            ld9<S>(cur, CV, cv);
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int j = 0; j < 3; j++)
-#pragma unroll
-                    for (int m = 0; m < 3; m++) M[3 * i + j] = fma(C[3 * i + m], cv[3 * m + j], M[3 * i + j]);
-        }
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = i; j < 3; j++)
-                commit<STAGE, S>(M[3 * i + j] + M[3 * j + i] + (i == j ? q_a : 0.0), VV + sym3(i, j), P, cur, acc, cs, dt6);
-    }
-    CPI_SECTION();
-    if (MODEL == 2 && STAGE < 4) {
-        // ---- cv (transient):  k = P_ctheta A^T + P_cc C^T ;  P_cc = P_theta,theta at step start (constant), base = P_vtheta^T
-        double ct[9], cc[9];
-        ld9<S>(cur, CT, ct); ldsym<S>(P, TT, cc);
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                double s = 0.0;
-#pragma unroll
-                for (int m = 0; m < 3; m++) s = fma(ct[3 * i + m], A[3 * j + m], s);
-#pragma unroll
-                for (int m = 0; m < 3; m++) s = fma(cc[3 * i + m], C[3 * j + m], s);
-                SM(cur, CV + 3 * i + j) = fma(s, cs, SM(P, VT + 3 * j + i));
-            }
-        CPI_SECTION();
-    }
-    {   // ---- vtheta:  k = A P_tt + P_vtheta W - P_vg (+ C P_ctheta)
-        double vt[9], tt[9], vg[9];
-        ld9<S>(src, VT, vt); ldsym<S>(src, TT, tt); ld9<S>(src, VG, vg);
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            double c3[3];
-            cross(&vt[3 * i], w, c3);
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                double s = c3[j] - vg[3 * i + j];
-#pragma unroll
-                for (int m = 0; m < 3; m++) s = fma(A[3 * i + m], tt[3 * m + j], s);
-                k[3 * i + j] = s;
-            }
-        }
-        if (MODEL == 2) {
-            double ct[9];
-            ld9<S>(cur, CT, ct);
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int j = 0; j < 3; j++)
-#pragma unroll
-                    for (int m = 0; m < 3; m++) k[3 * i + j] = fma(C[3 * i + m], ct[3 * m + j], k[3 * i + j]);
-            // ---- ctheta (transient):  k = P_ctheta W - P_cg ;  P_cg = P_theta,bg at step start (constant), base = P_tt
-            if (STAGE < 4) {
-                double cg[9], bt[9];
-                ld9<S>(P, TG, cg); ldsym<S>(P, TT, bt);
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    double c3[3];
-                    cross(&ct[3 * i], w, c3);
-#pragma unroll
-                    for (int j = 0; j < 3; j++) SM(cur, CT + 3 * i + j) = fma(c3[j] - cg[3 * i + j], cs, bt[3 * i + j]);
-                }
-            }
-        }
-        commit9<STAGE, S>(k, VT, P, cur, acc, cs, dt6);
-    }
-    CPI_SECTION();
-    {   // ---- va:  k = paa * B
-#pragma unroll
-        for (int e = 0; e < 9; e++) k[e] = paa_s * B[e];
-        commit9<STAGE, S>(k, VA, P, cur, acc, cs, dt6);
-    }
-    CPI_SECTION();
-    {   // ---- vg:  k = A P_tg (+ C P_cg, P_cg = P_theta,bg at step start)
-        double tg[9];
-        ld9<S>(src, TG, tg);
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                double s = 0.0;
-#pragma unroll
-                for (int m = 0; m < 3; m++) s = fma(A[3 * i + m], tg[3 * m + j], s);
-                k[3 * i + j] = s;
-            }
-        if (MODEL == 2) {
-            double cg[9];
-            ld9<S>(P, TG, cg);
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int j = 0; j < 3; j++)
-#pragma unroll
-                    for (int m = 0; m < 3; m++) k[3 * i + j] = fma(C[3 * i + m], cg[3 * m + j], k[3 * i + j]);
-        }
-        commit9<STAGE, S>(k, VG, P, cur, acc, cs, dt6);
-    }
-    CPI_SECTION();
-    {   // ---- tt:  k = M + M^T + q_w I,  M = -W P_tt - P_tg^T     (-W x = x cross w, column-wise)
-        //      tg:  k = -W P_tg - pgg I
-        double tt[9], tg[9], M[9];
-        ldsym<S>(src, TT, tt); ld9<S>(src, TG, tg);
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            double col[3] = {tt[j], tt[3 + j], tt[6 + j]}, c3[3];
-            cross(col, w, c3);
-#pragma unroll
-            for (int i = 0; i < 3; i++) M[3 * i + j] = c3[i] - tg[3 * j + i];
-        }
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = i; j < 3; j++)
-                commit<STAGE, S>(M[3 * i + j] + M[3 * j + i] + (i == j ? q_w : 0.0), TT + sym3(i, j), P, cur, acc, cs, dt6);
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            double col[3] = {tg[j], tg[3 + j], tg[6 + j]}, c3[3];
-            cross(col, w, c3);
-#pragma unroll
-            for (int i = 0; i < 3; i++) k[3 * i + j] = c3[i] - (i == j ? pgg_s : 0.0);
-        }
-        commit9<STAGE, S>(k, TG, P, cur, acc, cs, dt6);
-    }
-    CPI_SECTION();
+    for (int e = 0; e < 9; e++) SM(b, off + e) = x[e];
 }
+template <int S> CPI_DEV void ldst9(const double* Po, int off, const double* sl, int slot, int s, double* x) {
+    if (s == 0) ld9<S>(Po, off, x); else ld9<S>(sl, slot + (s - 1) * 9, x);
+}
+template <int S> CPI_DEV void ldstsym(const double* Po, int off, const double* sl, int slot, int s, double* x) {
+    if (s == 0) ldsym<S>(Po, off, x); else ldsym<S>(sl, slot + (s - 1) * 6, x);
+}
+CPI_DEV void sym_expand(const double* a, double* x) { x[0] = a[0]; x[1] = a[1]; x[2] = a[2]; x[3] = a[1]; x[4] = a[3]; x[5] = a[4]; x[6] = a[2]; x[7] = a[4]; x[8] = a[5]; }
 
 // rows of  -R^T [a x] : row i = a cross r_i  with r_i = column i of R (R row-major)
 CPI_DEV void make_A(const double* R, const double* a, double* A) {
@@ -345,6 +146,372 @@ CPI_DEV void make_B(const double* R, double* B) {   // -R^T
 #pragma unroll
         for (int j = 0; j < 3; j++) B[3 * i + j] = -R[3 * j + i];
 }
+
+
+template <int MODEL, int S>
+CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double* w, const double* ah, const double* gt,
+                         const double* R, const double* Rm, const double* R1, double pgg, double paa, double dt,
+                         double q_w, double q_wb, double q_a, double q_ab) {
+    const double hdt = dt * 0.5, dt6 = dt / 6.0;
+    constexpr int SL_TG = SLOT_A, SL_TT = SLOT_B, SL_VG = SLOT_C, SL_CT = SLOT_A, SL_CV = SLOT_B, SL_VA = SLOT_C, SL_VV = SLOT_D;
+    constexpr int SL_VT = (MODEL == 1) ? SLOT_A : SLOT_E, SL_PT = (MODEL == 1) ? SLOT_B : SLOT_A, SL_PV = (MODEL == 1) ? SLOT_A : SLOT_E;
+
+    {   // ---- tg:  k = -W x - pgg_s I        (-W c = c cross w, column-wise)
+        double x1[9], x[9], ks[9], k[9];
+        ld9<S>(Po, TG, x1);
+#pragma unroll
+        for (int e = 0; e < 9; e++) x[e] = x1[e];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const double pg_s = (s == 0) ? pgg : fma(q_wb, (s == 3 ? dt : hdt), pgg);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const double col[3] = {x[j], x[3 + j], x[6 + j]};
+                double c3[3];
+                cross(col, w, c3);
+#pragma unroll
+                for (int i = 0; i < 3; i++) k[3 * i + j] = c3[i] - (i == j ? pg_s : 0.0);
+            }
+#pragma unroll
+            for (int e = 0; e < 9; e++) ks[e] = KSUM(ks[e], k[e], s);
+            if (s < 3) {
+#pragma unroll
+                for (int e = 0; e < 9; e++) x[e] = fma(k[e], CN(s), x1[e]);
+                st9<S>(sl, SL_TG + s * 9, x);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 9; e++) SM(Pn, TG + e) = fma(dt6, ks[e], x1[e]);
+    }
+    CPI_SECTION();
+    {   // ---- tt:  k = M + M^T + q_w I,  M = -W x - P_tg^T
+        double a1[6], a[6], ks[6], x[9], M[9], tg[9];
+#pragma unroll
+        for (int e = 0; e < 6; e++) a[e] = a1[e] = SM(Po, TT + e);
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            sym_expand(a, x);
+            ldst9<S>(Po, TG, sl, SL_TG, s, tg);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const double col[3] = {x[j], x[3 + j], x[6 + j]};
+                double c3[3];
+                cross(col, w, c3);
+#pragma unroll
+                for (int i = 0; i < 3; i++) M[3 * i + j] = c3[i] - tg[3 * j + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = i; j < 3; j++) {
+                    const double kk = M[3 * i + j] + M[3 * j + i] + (i == j ? q_w : 0.0);
+                    ks[sym3(i, j)] = KSUM(ks[sym3(i, j)], kk, s);
+                    if (s < 3) { a[sym3(i, j)] = fma(kk, CN(s), a1[sym3(i, j)]); SM(sl, SL_TT + s * 6 + sym3(i, j)) = a[sym3(i, j)]; }
+                }
+        }
+#pragma unroll
+        for (int e = 0; e < 6; e++) SM(Pn, TT + e) = fma(dt6, ks[e], a1[e]);
+    }
+    CPI_SECTION();
+    {   // ---- vg:  k = A_s P_tg,s (+ C_s P_cg, P_cg = P_tg at step start)    and pg:  k = P_vg,s  (pure integral of vg's stage values)
+        double x1[9], x[9], ks[9], k[9], pg1[9], pgs[9], tg[9], A[9], C[9], cg[9];
+        ld9<S>(Po, VG, x1); ld9<S>(Po, PG, pg1);
+        if (MODEL == 2) ld9<S>(Po, TG, cg);
+#pragma unroll
+        for (int e = 0; e < 9; e++) x[e] = x1[e];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            if (s != 2) { make_A(RS(s), ah, A); if (MODEL == 2) make_A(RS(s), gt, C); }
+            ldst9<S>(Po, TG, sl, SL_TG, s, tg);
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int m = 0; m < 3; m++) t = fma(A[3 * i + m], tg[3 * m + j], t);
+                    if (MODEL == 2) {
+#pragma unroll
+                        for (int m = 0; m < 3; m++) t = fma(C[3 * i + m], cg[3 * m + j], t);
+                    }
+                    k[3 * i + j] = t;
+                }
+#pragma unroll
+            for (int e = 0; e < 9; e++) { ks[e] = KSUM(ks[e], k[e], s); pgs[e] = KSUM(pgs[e], x[e], s); }
+            if (s < 3) {
+#pragma unroll
+                for (int e = 0; e < 9; e++) x[e] = fma(k[e], CN(s), x1[e]);
+                st9<S>(sl, SL_VG + s * 9, x);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 9; e++) { SM(Pn, VG + e) = fma(dt6, ks[e], x1[e]); SM(Pn, PG + e) = fma(dt6, pgs[e], pg1[e]); }
+    }
+    CPI_SECTION();
+    if (MODEL == 2) {
+        // ---- ct (transient clone rows x theta; starts as P_tt, CpiV2.h:436-441):  k = x W - P_cg ;  only its stage values matter
+        double x1[9], x[9], cg[9];
+        ldsym<S>(Po, TT, x1); ld9<S>(Po, TG, cg);
+#pragma unroll
+        for (int e = 0; e < 9; e++) x[e] = x1[e];
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+            double k[9];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                double c3[3];
+                cross(&x[3 * i], w, c3);
+#pragma unroll
+                for (int j = 0; j < 3; j++) k[3 * i + j] = c3[j] - cg[3 * i + j];
+            }
+#pragma unroll
+            for (int e = 0; e < 9; e++) x[e] = fma(k[e], CN(s), x1[e]);
+            st9<S>(sl, SL_CT + s * 9, x);
+        }
+        CPI_SECTION();
+    }
+    {   // ---- vt:  k = A_s P_tt,s + x W - P_vg,s (+ C_s P_ct,s)
+        double x1[9], x[9], ks[9], k[9], tt[9], vg[9], A[9], C[9], ct[9];
+        ld9<S>(Po, VT, x1);
+#pragma unroll
+        for (int e = 0; e < 9; e++) x[e] = x1[e];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            if (s != 2) { make_A(RS(s), ah, A); if (MODEL == 2) make_A(RS(s), gt, C); }
+            ldstsym<S>(Po, TT, sl, SL_TT, s, tt);
+            ldst9<S>(Po, VG, sl, SL_VG, s, vg);
+            if (MODEL == 2) { if (s == 0) ldsym<S>(Po, TT, ct); else ld9<S>(sl, SL_CT + (s - 1) * 9, ct); }
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                double c3[3];
+                cross(&x[3 * i], w, c3);
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    double t = c3[j] - vg[3 * i + j];
+#pragma unroll
+                    for (int m = 0; m < 3; m++) t = fma(A[3 * i + m], tt[3 * m + j], t);
+                    if (MODEL == 2) {
+#pragma unroll
+                        for (int m = 0; m < 3; m++) t = fma(C[3 * i + m], ct[3 * m + j], t);
+                    }
+                    k[3 * i + j] = t;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 9; e++) ks[e] = KSUM(ks[e], k[e], s);
+            if (s < 3) {
+#pragma unroll
+                for (int e = 0; e < 9; e++) x[e] = fma(k[e], CN(s), x1[e]);
+                st9<S>(sl, SL_VT + s * 9, x);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 9; e++) SM(Pn, VT + e) = fma(dt6, ks[e], x1[e]);
+    }
+    CPI_SECTION();
+    if (MODEL == 2) {
+        // ---- cv (transient; starts as P_theta,v = P_vt^T):  k = P_ct,s A_s^T + P_cc C_s^T,  P_cc = P_tt at step start
+        double x1[9], cc[9], A[9], C[9];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) x1[3 * i + j] = SM(Po, VT + 3 * j + i);
+        ldsym<S>(Po, TT, cc);
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+            double ct[9], x[9];
+            if (s != 2) { make_A(RS(s), ah, A); make_A(RS(s), gt, C); }
+            if (s == 0) ldsym<S>(Po, TT, ct); else ld9<S>(sl, SL_CT + (s - 1) * 9, ct);
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int m = 0; m < 3; m++) t = fma(ct[3 * i + m], A[3 * j + m], t);
+#pragma unroll
+                    for (int m = 0; m < 3; m++) t = fma(cc[3 * i + m], C[3 * j + m], t);
+                    x[3 * i + j] = fma(t, CN(s), x1[3 * i + j]);
+                }
+            st9<S>(sl, SL_CV + s * 9, x);
+        }
+        CPI_SECTION();
+    }
+    {   // ---- pt:  k = P_vt,s + x W - P_pg,s ;  P_pg,s = P_pg + CN(s-1) P_vg,s-1  (recomputed, not stored)
+        double x1[9], x[9], ks[9], k[9], vt[9], pg1[9], pg[9], vgp[9];
+        ld9<S>(Po, PT, x1); ld9<S>(Po, PG, pg1);
+#pragma unroll
+        for (int e = 0; e < 9; e++) { x[e] = x1[e]; pg[e] = pg1[e]; }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            ldst9<S>(Po, VT, sl, SL_VT, s, vt);
+            if (s > 0) {
+                ldst9<S>(Po, VG, sl, SL_VG, s - 1, vgp);
+#pragma unroll
+                for (int e = 0; e < 9; e++) pg[e] = fma(vgp[e], CN(s - 1), pg1[e]);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                double c3[3];
+                cross(&x[3 * i], w, c3);
+#pragma unroll
+                for (int j = 0; j < 3; j++) k[3 * i + j] = vt[3 * i + j] + c3[j] - pg[3 * i + j];
+            }
+#pragma unroll
+            for (int e = 0; e < 9; e++) ks[e] = KSUM(ks[e], k[e], s);
+            if (s < 3) {
+#pragma unroll
+                for (int e = 0; e < 9; e++) x[e] = fma(k[e], CN(s), x1[e]);
+                st9<S>(sl, SL_PT + s * 9, x);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 9; e++) SM(Pn, PT + e) = fma(dt6, ks[e], x1[e]);
+    }
+    CPI_SECTION();
+    {   // ---- va:  k = paa_s B_s      and pa:  k = P_va,s
+        double x1[9], x[9], ks[9], pa1[9], pas[9], B[9];
+        ld9<S>(Po, VA, x1); ld9<S>(Po, PA, pa1);
+#pragma unroll
+        for (int e = 0; e < 9; e++) x[e] = x1[e];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const double pa_s = (s == 0) ? paa : fma(q_ab, (s == 3 ? dt : hdt), paa);
+            if (s != 2) make_B(RS(s), B);
+#pragma unroll
+            for (int e = 0; e < 9; e++) {
+                const double kk = pa_s * B[e];
+                ks[e] = KSUM(ks[e], kk, s);
+                pas[e] = KSUM(pas[e], x[e], s);
+                if (s < 3) x[e] = fma(kk, CN(s), x1[e]);
+            }
+            if (s < 3) st9<S>(sl, SL_VA + s * 9, x);
+        }
+#pragma unroll
+        for (int e = 0; e < 9; e++) { SM(Pn, VA + e) = fma(dt6, ks[e], x1[e]); SM(Pn, PA + e) = fma(dt6, pas[e], pa1[e]); }
+    }
+    CPI_SECTION();
+    {   // ---- vv:  k = M + M^T + q_a I,  M = A_s P_vt,s^T + B_s P_va,s^T (+ C_s P_cv,s)
+        double a1[6], ks[6], M[9], vt[9], va[9], A[9], B[9], C[9], cv[9];
+#pragma unroll
+        for (int e = 0; e < 6; e++) a1[e] = SM(Po, VV + e);
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            if (s != 2) { make_A(RS(s), ah, A); make_B(RS(s), B); if (MODEL == 2) make_A(RS(s), gt, C); }
+            ldst9<S>(Po, VT, sl, SL_VT, s, vt);
+            ldst9<S>(Po, VA, sl, SL_VA, s, va);
+            if (MODEL == 2) {
+                if (s == 0) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++)
+#pragma unroll
+                        for (int j = 0; j < 3; j++) cv[3 * i + j] = vt[3 * j + i];      // P_theta,v = P_vt^T
+                } else ld9<S>(sl, SL_CV + (s - 1) * 9, cv);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int m = 0; m < 3; m++) t = fma(A[3 * i + m], vt[3 * j + m], t);
+#pragma unroll
+                    for (int m = 0; m < 3; m++) t = fma(B[3 * i + m], va[3 * j + m], t);
+                    if (MODEL == 2) {
+#pragma unroll
+                        for (int m = 0; m < 3; m++) t = fma(C[3 * i + m], cv[3 * m + j], t);
+                    }
+                    M[3 * i + j] = t;
+                }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = i; j < 3; j++) {
+                    const double kk = M[3 * i + j] + M[3 * j + i] + (i == j ? q_a : 0.0);
+                    ks[sym3(i, j)] = KSUM(ks[sym3(i, j)], kk, s);
+                    if (s < 3) SM(sl, SL_VV + s * 6 + sym3(i, j)) = fma(kk, CN(s), a1[sym3(i, j)]);
+                }
+        }
+#pragma unroll
+        for (int e = 0; e < 6; e++) SM(Pn, VV + e) = fma(dt6, ks[e], a1[e]);
+    }
+    CPI_SECTION();
+    {   // ---- pv:  k = P_vv,s + P_pt,s A_s^T + P_pa,s B_s^T (+ P_cp,s^T C_s^T);  P_pa,s and P_cp,s recomputed from va / cv stage values
+        double x1[9], ks[9], k[9], vv[9], pt[9], pa1[9], pa[9], prev[9], A[9], B[9], C[9], cp1[9], cp[9];
+        ld9<S>(Po, PV, x1); ld9<S>(Po, PA, pa1);
+#pragma unroll
+        for (int e = 0; e < 9; e++) pa[e] = pa1[e];
+        if (MODEL == 2) {
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) cp[3 * i + j] = cp1[3 * i + j] = SM(Po, PT + 3 * j + i);     // P_theta,p = P_pt^T
+        }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            if (s != 2) { make_A(RS(s), ah, A); make_B(RS(s), B); if (MODEL == 2) make_A(RS(s), gt, C); }
+            ldstsym<S>(Po, VV, sl, SL_VV, s, vv);
+            ldst9<S>(Po, PT, sl, SL_PT, s, pt);
+            if (s > 0) {
+                ldst9<S>(Po, VA, sl, SL_VA, s - 1, prev);
+#pragma unroll
+                for (int e = 0; e < 9; e++) pa[e] = fma(prev[e], CN(s - 1), pa1[e]);
+                if (MODEL == 2) {
+                    if (s == 1) {
+#pragma unroll
+                        for (int i = 0; i < 3; i++)
+#pragma unroll
+                            for (int j = 0; j < 3; j++) prev[3 * i + j] = SM(Po, VT + 3 * j + i);     // cv stage 1 = P_vt^T
+                    } else ld9<S>(sl, SL_CV + (s - 2) * 9, prev);
+#pragma unroll
+                    for (int e = 0; e < 9; e++) cp[e] = fma(prev[e], CN(s - 1), cp1[e]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    double t = vv[3 * i + j];
+#pragma unroll
+                    for (int m = 0; m < 3; m++) t = fma(pt[3 * i + m], A[3 * j + m], t);
+#pragma unroll
+                    for (int m = 0; m < 3; m++) t = fma(pa[3 * i + m], B[3 * j + m], t);
+                    if (MODEL == 2) {
+#pragma unroll
+                        for (int m = 0; m < 3; m++) t = fma(cp[3 * m + i], C[3 * j + m], t);
+                    }
+                    k[3 * i + j] = t;
+                }
+#pragma unroll
+            for (int e = 0; e < 9; e++) {
+                ks[e] = KSUM(ks[e], k[e], s);
+                if (s < 3) SM(sl, SL_PV + s * 9 + e) = fma(k[e], CN(s), x1[e]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 9; e++) SM(Pn, PV + e) = fma(dt6, ks[e], x1[e]);
+    }
+    CPI_SECTION();
+    {   // ---- pp:  k = P_pv,s + P_pv,s^T
+        double a1[6], ks[6], pv[9];
+#pragma unroll
+        for (int e = 0; e < 6; e++) a1[e] = SM(Po, PP + e);
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            ldst9<S>(Po, PV, sl, SL_PV, s, pv);
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = i; j < 3; j++) ks[sym3(i, j)] = KSUM(ks[sym3(i, j)], pv[3 * i + j] + pv[3 * j + i], s);
+        }
+#pragma unroll
+        for (int e = 0; e < 6; e++) SM(Pn, PP + e) = fma(dt6, ks[e], a1[e]);
+    }
+    CPI_SECTION();
+}
+#undef CN
+#undef RS
+#undef KSUM
 
 // I - a W + b W2 applied to R:  out = (I - a [w x] + b [w x]^2) R
 CPI_DEV void rot_apply(double a, double b, const double* w, const double* R, double* out) {
@@ -372,10 +539,10 @@ __global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
     const int64_t win = (int64_t)blockIdx.x * p.wpb + tid;
     if (tid >= p.wpb || win >= p.n_windows) return;
 
-    double* P = smem + tid;
-    double* acc = P + (size_t)T::OFF_ACC * S;
-    double* cur = P + (size_t)T::OFF_CUR * S;
-    double* Jt = P + (size_t)T::OFF_J * S;                       // analytic Jacobians, or Discrete_J_b blocks (model 2 default)
+    double* P = smem + tid;                                       // current covariance tile (ping-pongs with Pn every step)
+    double* Pn = P + (size_t)T::OFF_PB * S;
+    double* sl = smem + tid + (size_t)T::OFF_SL * S;              // RK4 stage-value slots
+    double* Jt = smem + tid + (size_t)T::OFF_J * S;               // analytic Jacobians, or Discrete_J_b blocks (model 2 default)
     double* buf = smem + (size_t)T::ELEMS * S + (size_t)tid * (2 * BUF_DOUBLES);
     const uint32_t bar0 = smem_u32(smem + (size_t)(T::ELEMS + 2 * BUF_DOUBLES) * S + 2 * tid);
 
@@ -617,41 +784,10 @@ __global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
             }
         }
 
-        // ---- covariance: 4 RK4 stages on the block-sparse Lyapunov operator (CpiV1.h:272-353; CpiV2.h:326-422)
+        // ---- covariance: the reference's RK4, block-serial on the block-triangular Lyapunov operator (rk4_cascade)
         const double hdt = dt * 0.5, dt6 = dt / 6.0;
-        double A[9], B[9], C[9];
-        if (MODEL == 2) {
-            // clone rows start as copies of the theta rows (B_k of the previous step, CpiV2.h:436-441)
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    SM(cur, CT + 3 * i + j) = SM(P, TT + sym3(i, j));
-                    SM(cur, CV + 3 * i + j) = SM(P, VT + 3 * j + i);
-                    SM(cur, CP + 3 * i + j) = SM(P, PT + 3 * j + i);
-                }
-        }
-        make_A(R, ah, A); make_B(R, B);
-        if (MODEL == 2) make_A(R, g_tau, C);
-        rk4_stage<1, MODEL, S>(P, cur, acc, wh, A, B, C, pgg, paa, hdt, dt6, p.q_w, p.q_a);
-        make_A(Rm, ah, A); make_B(Rm, B);
-        if (MODEL == 2) make_A(Rm, g_tau, C);
-        {
-            const double pgg2 = fma(p.q_wb, hdt, pgg), paa2 = fma(p.q_ab, hdt, paa);
-            rk4_stage<2, MODEL, S>(P, cur, acc, wh, A, B, C, pgg2, paa2, hdt, dt6, p.q_w, p.q_a);
-            rk4_stage<3, MODEL, S>(P, cur, acc, wh, A, B, C, pgg2, paa2, dt, dt6, p.q_w, p.q_a);
-        }
-        double A1[9], C1[9];
-        if (MODEL == 2 && !ANALYTIC) {
-#pragma unroll
-            for (int e = 0; e < 9; e++) { A1[e] = A[e]; C1[e] = C[e]; }   // keep the mid-point blocks for Phi
-        }
-        make_A(R1, ah, A); make_B(R1, B);
-        if (MODEL == 2) make_A(R1, g_tau, C);
-        {
-            const double pgg4 = fma(p.q_wb, dt, pgg), paa4 = fma(p.q_ab, dt, paa);
-            rk4_stage<4, MODEL, S>(P, cur, acc, wh, A, B, C, pgg4, paa4, dt, dt6, p.q_w, p.q_a);
-        }
+        rk4_cascade<MODEL, S>(P, Pn, sl, wh, ah, g_tau, R, Rm, R1, pgg, paa, dt, p.q_w, p.q_wb, p.q_a, p.q_ab);
+        { double* t = P; P = Pn; Pn = t; }
         pgg += dt6 * (p.q_wb + 2.0 * p.q_wb + 2.0 * p.q_wb + p.q_wb);
         paa += dt6 * (p.q_ab + 2.0 * p.q_ab + 2.0 * p.q_ab + p.q_ab);
 
@@ -659,8 +795,10 @@ __global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
             // ---- Discrete_J_b <- B_k * Phi * Discrete_J_b restricted to the consumed columns (CpiV2.h:347-426, 443).
             // Phi's RK4 (Phi_dot = F Phi, Phi(0) = I) in block form; stage matrices F1 (R_old), F2 = F3 (R_mid), F4 (R_new).
             // Row theta:  X' = -W X (- I for the bg column).   Row v: sum_s A_s X_theta,s + B_s/C_s/L_s.   Row p: integral of row v.
-            double A0[9], C0[9];
+            double A0[9], C0[9], A1[9], C1[9], A[9], C[9], B[9];
             make_A(R, ah, A0); make_A(R, g_tau, C0);
+            make_A(Rm, ah, A1); make_A(Rm, g_tau, C1);
+            make_A(R1, ah, A); make_A(R1, g_tau, C); make_B(R1, B);
             double Xtt[4][9], Xtg[4][9];   // stage VALUES Phi_s (s = 1..4) of the two theta-row blocks
             double ktt[4][9], ktg[4][9];   // stage DERIVATIVES
 #pragma unroll
