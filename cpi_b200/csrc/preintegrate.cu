@@ -391,38 +391,51 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
         for (int e = 0; e < 9; e++) { SM(Pn, VA + e) = fma(dt6, ks[e], x1[e]); SM(Pn, PA + e) = fma(dt6, pas[e], pa1[e]); }
     }
     CPI_SECTION();
-    {   // ---- vv:  k = M + M^T + q_a I,  M = A_s P_vt,s^T + B_s P_va,s^T (+ C_s P_cv,s)
-        double a1[6], ks[6], M[9], vt[9], va[9], A[9], B[9], C[9], cv[9];
+    {   // ---- vv:  k = M + M^T + q_a I,  M = A_s P_vt,s^T + B_s P_va,s^T (+ C_s P_cv,s),  B_s = -R_s^T used straight from R_s.
+        //      Terms are accumulated in fenced passes so that only one operand pair is live at a time.
+        double a1[6], ks[6], M[9];
 #pragma unroll
         for (int e = 0; e < 6; e++) a1[e] = SM(Po, VV + e);
 #pragma unroll
         for (int s = 0; s < 4; s++) {
-            if (s != 2) { make_A(RS(s), ah, A); make_B(RS(s), B); if (MODEL == 2) make_A(RS(s), gt, C); }
-            ldst9<S>(Po, VT, sl, SL_VT, s, vt);
-            ldst9<S>(Po, VA, sl, SL_VA, s, va);
+            {
+                double A[9], vt[9];
+                make_A(RS(s), ah, A);
+                ldst9<S>(Po, VT, sl, SL_VT, s, vt);
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++) M[3 * i + j] = A[3 * i] * vt[3 * j] + A[3 * i + 1] * vt[3 * j + 1] + A[3 * i + 2] * vt[3 * j + 2];
+            }
+            CPI_SECTION();
+            {
+                double va[9];
+                const double* Rs = RS(s);
+                ldst9<S>(Po, VA, sl, SL_VA, s, va);
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++)
+#pragma unroll
+                        for (int m = 0; m < 3; m++) M[3 * i + j] = fma(-Rs[3 * m + i], va[3 * j + m], M[3 * i + j]);
+            }
             if (MODEL == 2) {
+                CPI_SECTION();
+                double C[9], cv[9];
+                make_A(RS(s), gt, C);
                 if (s == 0) {
 #pragma unroll
                     for (int i = 0; i < 3; i++)
 #pragma unroll
-                        for (int j = 0; j < 3; j++) cv[3 * i + j] = vt[3 * j + i];      // P_theta,v = P_vt^T
+                        for (int j = 0; j < 3; j++) cv[3 * i + j] = SM(Po, VT + 3 * j + i);      // P_theta,v = P_vt^T
                 } else ld9<S>(sl, SL_CV + (s - 1) * 9, cv);
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++)
+#pragma unroll
+                        for (int m = 0; m < 3; m++) M[3 * i + j] = fma(C[3 * i + m], cv[3 * m + j], M[3 * i + j]);
             }
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    double t = 0.0;
-#pragma unroll
-                    for (int m = 0; m < 3; m++) t = fma(A[3 * i + m], vt[3 * j + m], t);
-#pragma unroll
-                    for (int m = 0; m < 3; m++) t = fma(B[3 * i + m], va[3 * j + m], t);
-                    if (MODEL == 2) {
-#pragma unroll
-                        for (int m = 0; m < 3; m++) t = fma(C[3 * i + m], cv[3 * m + j], t);
-                    }
-                    M[3 * i + j] = t;
-                }
 #pragma unroll
             for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -431,32 +444,58 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
                     ks[sym3(i, j)] = KSUM(ks[sym3(i, j)], kk, s);
                     if (s < 3) SM(sl, SL_VV + s * 6 + sym3(i, j)) = fma(kk, CN(s), a1[sym3(i, j)]);
                 }
+            CPI_SECTION();
         }
 #pragma unroll
         for (int e = 0; e < 6; e++) SM(Pn, VV + e) = fma(dt6, ks[e], a1[e]);
     }
     CPI_SECTION();
-    {   // ---- pv:  k = P_vv,s + P_pt,s A_s^T + P_pa,s B_s^T (+ P_cp,s^T C_s^T);  P_pa,s and P_cp,s recomputed from va / cv stage values
-        double x1[9], ks[9], k[9], vv[9], pt[9], pa1[9], pa[9], prev[9], A[9], B[9], C[9], cp1[9], cp[9];
-        ld9<S>(Po, PV, x1); ld9<S>(Po, PA, pa1);
-#pragma unroll
-        for (int e = 0; e < 9; e++) pa[e] = pa1[e];
-        if (MODEL == 2) {
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int j = 0; j < 3; j++) cp[3 * i + j] = cp1[3 * i + j] = SM(Po, PT + 3 * j + i);     // P_theta,p = P_pt^T
-        }
+    {   // ---- pv:  k = P_vv,s + P_pt,s A_s^T + P_pa,s B_s^T (+ P_cp,s^T C_s^T);  P_pa,s = P_pa + CN(s-1) P_va,s-1 and
+        //      P_cp,s = P_pt^T + CN(s-1) P_cv,s-1 are recomputed from the va / cv stage values instead of being stored
+        double x1[9], ks[9], k[9];
+        ld9<S>(Po, PV, x1);
 #pragma unroll
         for (int s = 0; s < 4; s++) {
-            if (s != 2) { make_A(RS(s), ah, A); make_B(RS(s), B); if (MODEL == 2) make_A(RS(s), gt, C); }
-            ldstsym<S>(Po, VV, sl, SL_VV, s, vv);
-            ldst9<S>(Po, PT, sl, SL_PT, s, pt);
-            if (s > 0) {
-                ldst9<S>(Po, VA, sl, SL_VA, s - 1, prev);
+            {
+                double A[9], pt[9];
+                ldstsym<S>(Po, VV, sl, SL_VV, s, k);
+                make_A(RS(s), ah, A);
+                ldst9<S>(Po, PT, sl, SL_PT, s, pt);
 #pragma unroll
-                for (int e = 0; e < 9; e++) pa[e] = fma(prev[e], CN(s - 1), pa1[e]);
-                if (MODEL == 2) {
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++)
+#pragma unroll
+                        for (int m = 0; m < 3; m++) k[3 * i + j] = fma(pt[3 * i + m], A[3 * j + m], k[3 * i + j]);
+            }
+            CPI_SECTION();
+            {
+                double pa[9];
+                const double* Rs = RS(s);
+                ld9<S>(Po, PA, pa);
+                if (s > 0) {
+                    double prev[9];
+                    ldst9<S>(Po, VA, sl, SL_VA, s - 1, prev);
+#pragma unroll
+                    for (int e = 0; e < 9; e++) pa[e] = fma(prev[e], CN(s - 1), pa[e]);
+                }
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++)
+#pragma unroll
+                        for (int m = 0; m < 3; m++) k[3 * i + j] = fma(pa[3 * i + m], -Rs[3 * m + j], k[3 * i + j]);
+            }
+            if (MODEL == 2) {
+                CPI_SECTION();
+                double C[9], cp[9];
+                make_A(RS(s), gt, C);
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++) cp[3 * i + j] = SM(Po, PT + 3 * j + i);     // P_theta,p = P_pt^T
+                if (s > 0) {
+                    double prev[9];
                     if (s == 1) {
 #pragma unroll
                         for (int i = 0; i < 3; i++)
@@ -464,29 +503,21 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
                             for (int j = 0; j < 3; j++) prev[3 * i + j] = SM(Po, VT + 3 * j + i);     // cv stage 1 = P_vt^T
                     } else ld9<S>(sl, SL_CV + (s - 2) * 9, prev);
 #pragma unroll
-                    for (int e = 0; e < 9; e++) cp[e] = fma(prev[e], CN(s - 1), cp1[e]);
+                    for (int e = 0; e < 9; e++) cp[e] = fma(prev[e], CN(s - 1), cp[e]);
                 }
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++)
+#pragma unroll
+                        for (int m = 0; m < 3; m++) k[3 * i + j] = fma(cp[3 * m + i], C[3 * j + m], k[3 * i + j]);
             }
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    double t = vv[3 * i + j];
-#pragma unroll
-                    for (int m = 0; m < 3; m++) t = fma(pt[3 * i + m], A[3 * j + m], t);
-#pragma unroll
-                    for (int m = 0; m < 3; m++) t = fma(pa[3 * i + m], B[3 * j + m], t);
-                    if (MODEL == 2) {
-#pragma unroll
-                        for (int m = 0; m < 3; m++) t = fma(cp[3 * m + i], C[3 * j + m], t);
-                    }
-                    k[3 * i + j] = t;
-                }
 #pragma unroll
             for (int e = 0; e < 9; e++) {
                 ks[e] = KSUM(ks[e], k[e], s);
                 if (s < 3) SM(sl, SL_PV + s * 9 + e) = fma(k[e], CN(s), x1[e]);
             }
+            CPI_SECTION();
         }
 #pragma unroll
         for (int e = 0; e < 9; e++) SM(Pn, PV + e) = fma(dt6, ks[e], x1[e]);
@@ -794,99 +825,131 @@ __global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
         if (MODEL == 2 && !ANALYTIC) {
             // ---- Discrete_J_b <- B_k * Phi * Discrete_J_b restricted to the consumed columns (CpiV2.h:347-426, 443).
             // Phi's RK4 (Phi_dot = F Phi, Phi(0) = I) in block form; stage matrices F1 (R_old), F2 = F3 (R_mid), F4 (R_new).
-            // Row theta:  X' = -W X (- I for the bg column).   Row v: sum_s A_s X_theta,s + B_s/C_s/L_s.   Row p: integral of row v.
-            double A0[9], C0[9], A1[9], C1[9], A[9], C[9], B[9];
-            make_A(R, ah, A0); make_A(R, g_tau, C0);
-            make_A(Rm, ah, A1); make_A(Rm, g_tau, C1);
-            make_A(R1, ah, A); make_A(R1, g_tau, C); make_B(R1, B);
-            double Xtt[4][9], Xtg[4][9];   // stage VALUES Phi_s (s = 1..4) of the two theta-row blocks
-            double ktt[4][9], ktg[4][9];   // stage DERIVATIVES
+            //   row theta:  X' = -W X (- I for the bg column)
+            //   row v:      k_s = A_s X_theta,s  (+ the direct blocks B_s, C_s, L_s for the identity rows of Phi)
+            //   row p:      k_s = (row v stage VALUE)_s = {0, hdt k_1, hdt k_2, dt k_3}
+            // Phi_v,X = dt/6 (k1 + 2k2 + 2k3 + k4),  Phi_p,X = dt/6 (2 hdt k1 + 2 hdt k2 + dt k3),  Phi_p,v = dt I.
+            // Done in fenced sections that park the theta-row stage values in the (now free) RK4 slots, so that the
+            // register allocator never sees more than ~60 live doubles.
+            const double Ppv = dt6 * (1.0 + 2.0 + 2.0 + 1.0);
+            {   // section 1: theta row.  X_tt,s -> slot A, X_tg,s -> slot B (s = 1..3);  D_tg' -> slot C (committed last)
+                double xtt[9], xtg[9], stt[9], stg[9], k1[9], k2[9];
 #pragma unroll
-            for (int e = 0; e < 9; e++) { Xtt[0][e] = (e % 4 == 0) ? 1.0 : 0.0; Xtg[0][e] = 0.0; }
+                for (int e = 0; e < 9; e++) { xtt[e] = (e % 4 == 0) ? 1.0 : 0.0; xtg[e] = 0.0; }
 #pragma unroll
-            for (int s = 0; s < 4; s++) {
+                for (int st = 0; st < 4; st++) {
 #pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    double col[3] = {Xtt[s][j], Xtt[s][3 + j], Xtt[s][6 + j]}, c3[3];
-                    cross(col, wh, c3);
-                    ktt[s][j] = c3[0]; ktt[s][3 + j] = c3[1]; ktt[s][6 + j] = c3[2];
-                    double col2[3] = {Xtg[s][j], Xtg[s][3 + j], Xtg[s][6 + j]};
-                    cross(col2, wh, c3);
-                    ktg[s][j] = c3[0] - (j == 0 ? 1.0 : 0.0); ktg[s][3 + j] = c3[1] - (j == 1 ? 1.0 : 0.0); ktg[s][6 + j] = c3[2] - (j == 2 ? 1.0 : 0.0);
-                }
-                if (s < 3) {
-                    const double cstep = (s == 2) ? dt : hdt;
+                    for (int j = 0; j < 3; j++) {
+                        const double col[3] = {xtt[j], xtt[3 + j], xtt[6 + j]}, col2[3] = {xtg[j], xtg[3 + j], xtg[6 + j]};
+                        double c3[3];
+                        cross(col, wh, c3);
+                        k1[j] = c3[0]; k1[3 + j] = c3[1]; k1[6 + j] = c3[2];
+                        cross(col2, wh, c3);
+                        k2[j] = c3[0] - (j == 0 ? 1.0 : 0.0); k2[3 + j] = c3[1] - (j == 1 ? 1.0 : 0.0); k2[6 + j] = c3[2] - (j == 2 ? 1.0 : 0.0);
+                    }
 #pragma unroll
                     for (int e = 0; e < 9; e++) {
-                        Xtt[s + 1][e] = ((e % 4 == 0) ? 1.0 : 0.0) + ktt[s][e] * cstep;
-                        Xtg[s + 1][e] = ktg[s][e] * cstep;
+                        stt[e] = (st == 0) ? k1[e] : (st == 3 ? stt[e] + k1[e] : stt[e] + 2.0 * k1[e]);
+                        stg[e] = (st == 0) ? k2[e] : (st == 3 ? stg[e] + k2[e] : stg[e] + 2.0 * k2[e]);
+                    }
+                    if (st < 3) {
+                        const double cstep = (st == 2) ? dt : hdt;
+#pragma unroll
+                        for (int e = 0; e < 9; e++) {
+                            xtt[e] = ((e % 4 == 0) ? 1.0 : 0.0) + k1[e] * cstep;
+                            xtg[e] = k2[e] * cstep;
+                            SM(sl, SLOT_A + st * 9 + e) = xtt[e];
+                            SM(sl, SLOT_B + st * 9 + e) = xtg[e];
+                        }
                     }
                 }
-            }
-            double Ptt[9], Ptg[9];   // Phi_theta,theta, Phi_theta,bg
+                double Dtg[9], n1[9];
+                ld9<S>(Jt, D_TG, Dtg);
 #pragma unroll
-            for (int e = 0; e < 9; e++) {
-                Ptt[e] = ((e % 4 == 0) ? 1.0 : 0.0) + dt6 * (ktt[0][e] + 2.0 * ktt[1][e] + 2.0 * ktt[2][e] + ktt[3][e]);
-                Ptg[e] = dt6 * (ktg[0][e] + 2.0 * ktg[1][e] + 2.0 * ktg[2][e] + ktg[3][e]);
+                for (int e = 0; e < 9; e++) { stt[e] = ((e % 4 == 0) ? 1.0 : 0.0) + dt6 * stt[e]; stg[e] = dt6 * stg[e]; }   // Phi_tt, Phi_tg
+                mul33(stt, Dtg, n1);
+#pragma unroll
+                for (int e = 0; e < 9; e++) SM(sl, SLOT_C + e) = n1[e] + stg[e];
             }
-            const double* As[4] = {A0, A1, A1, A};
-            const double* Cs[4] = {C0, C1, C1, C};
-            double B0[9], Bm[9];
-            make_B(R, B0); make_B(Rm, Bm);
-            const double* Bs[4] = {B0, Bm, Bm, B};
-            double L[4][9];                                 // L_s = -R_s^T R_old [g_k x]  (CpiV2.h:336)
-            {
+            CPI_SECTION();
+            {   // section 2: bg column of rows v and p
+                double swt[9], sut[9], swg[9], sug[9], A[9], X[9], k[9];
+#pragma unroll
+                for (int st = 0; st < 4; st++) {
+                    if (st != 2) make_A(st == 0 ? R : (st == 3 ? R1 : Rm), ah, A);
+                    // theta-theta column:  k = A_s X_tt,s   (X_tt,1 = I)
+                    if (st == 0) {
+#pragma unroll
+                        for (int e = 0; e < 9; e++) k[e] = A[e];
+                    } else { ld9<S>(sl, SLOT_A + (st - 1) * 9, X); mul33(A, X, k); }
+#pragma unroll
+                    for (int e = 0; e < 9; e++) {
+                        swt[e] = (st == 0) ? k[e] : (st == 3 ? swt[e] + k[e] : swt[e] + 2.0 * k[e]);
+                        if (st < 3) sut[e] = (st == 0) ? 2.0 * (k[e] * hdt) : (st == 1 ? sut[e] + 2.0 * (k[e] * hdt) : sut[e] + k[e] * dt);
+                    }
+                    // theta-bg column:  k = A_s X_tg,s   (X_tg,1 = 0)
+                    if (st == 0) {
+#pragma unroll
+                        for (int e = 0; e < 9; e++) { swg[e] = 0.0; sug[e] = 2.0 * (0.0 * hdt); }
+                    } else {
+                        ld9<S>(sl, SLOT_B + (st - 1) * 9, X); mul33(A, X, k);
+#pragma unroll
+                        for (int e = 0; e < 9; e++) {
+                            swg[e] = (st == 3) ? swg[e] + k[e] : swg[e] + 2.0 * k[e];
+                            if (st < 3) sug[e] = (st == 1) ? sug[e] + 2.0 * (k[e] * hdt) : sug[e] + k[e] * dt;
+                        }
+                    }
+                }
+                double Pv[9], Pp[9];
+                {   // clone-column direct blocks  C_s = -R_s^T [g_tau x]  (three distinct values)
+                    double C0[9], Cm[9], C1[9];
+                    make_A(R, g_tau, C0); make_A(Rm, g_tau, Cm); make_A(R1, g_tau, C1);
+#pragma unroll
+                    for (int e = 0; e < 9; e++) {
+                        const double swc = C0[e] + 2.0 * Cm[e] + 2.0 * Cm[e] + C1[e];
+                        const double suc = 2.0 * (C0[e] * hdt) + 2.0 * (Cm[e] * hdt) + Cm[e] * dt;
+                        Pv[e] = dt6 * swt[e] + dt6 * swc;            // Phi_v,theta + Phi_v,c
+                        Pp[e] = dt6 * sut[e] + dt6 * suc;            // Phi_p,theta + Phi_p,c
+                    }
+                }
+                double Dtg[9], Dvg[9], Dpg[9], n2[9], n3[9];
+                ld9<S>(Jt, D_TG, Dtg); ld9<S>(Jt, D_VG, Dvg); ld9<S>(Jt, D_PG, Dpg);
+                mul33(Pv, Dtg, n2); mul33(Pp, Dtg, n3);
+#pragma unroll
+                for (int e = 0; e < 9; e++) {
+                    SM(Jt, D_PG + e) = n3[e] + dt6 * sug[e] + Ppv * Dvg[e] + Dpg[e];
+                    SM(Jt, D_VG + e) = n2[e] + dt6 * swg[e] + Dvg[e];
+                }
+            }
+            CPI_SECTION();
+            {   // section 3: ba and theta_klin columns (direct blocks):  Phi_v,a = dt/6 (B1 + 2 Bm + 2 Bm + B4),  Phi_v,l likewise with
+                // L_s = -R_s^T R_old [g_k x]  (CpiV2.h:336)
                 const double sk[9] = {0.0, -g_k[2], g_k[1], g_k[2], 0.0, -g_k[0], -g_k[1], g_k[0], 0.0};
-                double RS[9], t9[9];
+                double RS[9], L0[9], Lm[9], L1[9];
                 mul33(R, sk, RS);
-                mulT33(R, RS, t9);
+                mulT33(R, RS, L0); mulT33(Rm, RS, Lm); mulT33(R1, RS, L1);
 #pragma unroll
-                for (int e = 0; e < 9; e++) L[0][e] = -t9[e];
-                mulT33(Rm, RS, t9);
+                for (int i = 0; i < 3; i++)
 #pragma unroll
-                for (int e = 0; e < 9; e++) { L[1][e] = -t9[e]; L[2][e] = -t9[e]; }
-                mulT33(R1, RS, t9);
+                    for (int j = 0; j < 3; j++) {
+                        const int e = 3 * i + j;
+                        const double b0 = -R[3 * j + i], bm = -Rm[3 * j + i], b1 = -R1[3 * j + i];
+                        const double Pva = dt6 * (b0 + 2.0 * bm + 2.0 * bm + b1);
+                        const double Ppa = dt6 * (2.0 * (b0 * hdt) + 2.0 * (bm * hdt) + bm * dt);
+                        const double l0 = -L0[e], lm = -Lm[e], l1 = -L1[e];
+                        const double Pvl = dt6 * (l0 + 2.0 * lm + 2.0 * lm + l1);
+                        const double Ppl = dt6 * (2.0 * (l0 * hdt) + 2.0 * (lm * hdt) + lm * dt);
+                        const double dva = SM(Jt, D_VA + e), dvl = SM(Jt, D_VL + e);
+                        SM(Jt, D_PA + e) = Ppa + Ppv * dva + SM(Jt, D_PA + e);
+                        SM(Jt, D_VA + e) = Pva + dva;
+                        SM(Jt, D_PL + e) = Ppl + Ppv * dvl + SM(Jt, D_PL + e);
+                        SM(Jt, D_VL + e) = Pvl + dvl;
+                    }
+                // commit D_tg' (parked in slot C by section 1; sections 2 needed the old value)
 #pragma unroll
-                for (int e = 0; e < 9; e++) L[3][e] = -t9[e];
+                for (int e = 0; e < 9; e++) SM(Jt, D_TG + e) = SM(sl, SLOT_C + e);
             }
-            double kvt[4][9], kvg[4][9];
-#pragma unroll
-            for (int s = 0; s < 4; s++) { mul33(As[s], Xtt[s], kvt[s]); mul33(As[s], Xtg[s], kvg[s]); }
-            // Phi_v,X = dt/6 (k1 + 2k2 + 2k3 + k4);  Phi_p,X = dt/6 (X1 + 2 X2 + 2 X3 + X4) with X_s the v-row stage VALUES:
-            // X1 = 0, X2 = hdt k1, X3 = hdt k2, X4 = dt k3
-            double Pvt[9], Pvg[9], Pva[9], Pvc[9], Pvl[9], Ppt[9], Ppg[9], Ppa[9], Ppc[9], Ppl[9];
-#pragma unroll
-            for (int e = 0; e < 9; e++) {
-                Pvt[e] = dt6 * (kvt[0][e] + 2.0 * kvt[1][e] + 2.0 * kvt[2][e] + kvt[3][e]);
-                Pvg[e] = dt6 * (kvg[0][e] + 2.0 * kvg[1][e] + 2.0 * kvg[2][e] + kvg[3][e]);
-                Pva[e] = dt6 * (Bs[0][e] + 2.0 * Bs[1][e] + 2.0 * Bs[2][e] + Bs[3][e]);
-                Pvc[e] = dt6 * (Cs[0][e] + 2.0 * Cs[1][e] + 2.0 * Cs[2][e] + Cs[3][e]);
-                Pvl[e] = dt6 * (L[0][e] + 2.0 * L[1][e] + 2.0 * L[2][e] + L[3][e]);
-                Ppt[e] = dt6 * (2.0 * (kvt[0][e] * hdt) + 2.0 * (kvt[1][e] * hdt) + kvt[2][e] * dt);
-                Ppg[e] = dt6 * (2.0 * (kvg[0][e] * hdt) + 2.0 * (kvg[1][e] * hdt) + kvg[2][e] * dt);
-                Ppa[e] = dt6 * (2.0 * (Bs[0][e] * hdt) + 2.0 * (Bs[1][e] * hdt) + Bs[2][e] * dt);
-                Ppc[e] = dt6 * (2.0 * (Cs[0][e] * hdt) + 2.0 * (Cs[1][e] * hdt) + Cs[2][e] * dt);
-                Ppl[e] = dt6 * (2.0 * (L[0][e] * hdt) + 2.0 * (L[1][e] * hdt) + L[2][e] * dt);
-            }
-            const double Ppv = dt6 * (1.0 + 2.0 + 2.0 + 1.0);   // Phi_p,v = that * I
-            // apply: D' = B_k Phi D on columns {bg, ba, theta_klin}; D_c,X == D_theta,X (clone of the previous step)
-            double Dtg[9], Dvg[9], Dpg[9], Dva[9], Dpa[9], Dvl[9], Dpl[9], n1[9], n2[9], n3[9];
-            ld9<S>(Jt, D_TG, Dtg); ld9<S>(Jt, D_VG, Dvg); ld9<S>(Jt, D_PG, Dpg);
-            ld9<S>(Jt, D_VA, Dva); ld9<S>(Jt, D_PA, Dpa); ld9<S>(Jt, D_VL, Dvl); ld9<S>(Jt, D_PL, Dpl);
-            double Pvtc[9], Pptc[9];
-#pragma unroll
-            for (int e = 0; e < 9; e++) { Pvtc[e] = Pvt[e] + Pvc[e]; Pptc[e] = Ppt[e] + Ppc[e]; }
-            mul33(Ptt, Dtg, n1); mul33(Pvtc, Dtg, n2); mul33(Pptc, Dtg, n3);
-#pragma unroll
-            for (int e = 0; e < 9; e++) {
-                SM(Jt, D_PG + e) = n3[e] + Ppg[e] + Ppv * Dvg[e] + Dpg[e];
-                SM(Jt, D_VG + e) = n2[e] + Pvg[e] + Dvg[e];
-                SM(Jt, D_TG + e) = n1[e] + Ptg[e];
-                SM(Jt, D_PA + e) = Ppa[e] + Ppv * Dva[e] + Dpa[e];
-                SM(Jt, D_VA + e) = Pva[e] + Dva[e];
-                SM(Jt, D_PL + e) = Ppl[e] + Ppv * Dvl[e] + Dpl[e];
-                SM(Jt, D_VL + e) = Pvl[e] + Dvl[e];
-            }
+            CPI_SECTION();
         }
 
         // ---- commit rotation (CpiV1.h:357)
