@@ -101,7 +101,7 @@ int cpi_device_count(void) {
 int cpi_preintegrate_batch(int model, int dtype, int64_t n_windows, const int64_t* sample_offsets, int64_t ns_uniform,
                            const void* samples, const void* lin, const double* sigmas, int flags, void* out_records, void* stream) {
     if (model != 1 && model != 2) return fail(CPI_EINVAL, "model must be 1 or 2 (got %d)", model);
-    if (dtype != 64) return fail(CPI_EINVAL, "dtype %d not supported by this build (fp64 only)", dtype);
+    if (dtype != 64 && dtype != 32) return fail(CPI_EINVAL, "dtype must be 64 or 32 (got %d)", dtype);
     if (n_windows < 0 || (!sample_offsets && ns_uniform < 0)) return fail(CPI_EINVAL, "negative count");
     if (n_windows == 0) return CPI_OK;
     if (!lin || !sigmas || !out_records) return fail(CPI_EINVAL, "null pointer argument");
@@ -112,11 +112,11 @@ int cpi_preintegrate_batch(int model, int dtype, int64_t n_windows, const int64_
     if (rc) return rc;
     cpi::PreintParams p;
     p.n_windows = n_windows; p.offsets = sample_offsets; p.ns_uniform = ns_uniform;
-    p.samples = (const double*)samples; p.lin = (const double*)lin; p.out = (double*)out_records;
+    p.samples = samples; p.lin = lin; p.out = out_records;
     p.q_w = sigmas[0] * sigmas[0]; p.q_wb = sigmas[1] * sigmas[1]; p.q_a = sigmas[2] * sigmas[2]; p.q_ab = sigmas[3] * sigmas[3];
     p.wpb = 0;
     int launches = 0;
-    CU(cpi::preint_launch(model, flags, p, d.sms, d.max_smem, (cudaStream_t)stream, &launches));
+    CU(cpi::preint_launch(model, dtype, flags, p, d.sms, d.max_smem, (cudaStream_t)stream, &launches));
     g_launches += launches;
     return CPI_OK;
 }
@@ -124,7 +124,7 @@ int cpi_preintegrate_batch(int model, int dtype, int64_t n_windows, const int64_
 int cpi_preintegrate_batch_host(int model, int dtype, int64_t n_windows, const int64_t* sample_offsets, int64_t ns_uniform,
                                 const void* samples, const void* lin, const double* sigmas, int flags, void* out_records) {
     if (model != 1 && model != 2) return fail(CPI_EINVAL, "model must be 1 or 2 (got %d)", model);
-    if (dtype != 64) return fail(CPI_EINVAL, "dtype %d not supported by this build (fp64 only)", dtype);
+    if (dtype != 64 && dtype != 32) return fail(CPI_EINVAL, "dtype must be 64 or 32 (got %d)", dtype);
     if (n_windows < 0) return fail(CPI_EINVAL, "negative count");
     if (n_windows == 0) return CPI_OK;
     if (!lin || !sigmas || !out_records) return fail(CPI_EINVAL, "null pointer argument");
@@ -137,18 +137,19 @@ int cpi_preintegrate_batch_host(int model, int dtype, int64_t n_windows, const i
     if (rc) return rc;
     cudaStream_t st = g_scratch.stream;
     void *d_s, *d_l, *d_o, *d_off = nullptr;
-    if ((rc = dev_buf(0, (size_t)entries * CPI_SAMPLE_DOUBLES * 8, &d_s))) return rc;
-    if ((rc = dev_buf(1, (size_t)n_windows * CPI_LIN_DOUBLES * 8, &d_l))) return rc;
-    if ((rc = dev_buf(2, (size_t)n_windows * rd * 8, &d_o))) return rc;
+    const size_t es = dtype == 32 ? 4 : 8;
+    if ((rc = dev_buf(0, (size_t)entries * CPI_SAMPLE_DOUBLES * es + 16, &d_s))) return rc;
+    if ((rc = dev_buf(1, (size_t)n_windows * CPI_LIN_DOUBLES * es, &d_l))) return rc;
+    if ((rc = dev_buf(2, (size_t)n_windows * rd * es, &d_o))) return rc;
     if (sample_offsets) {
         if ((rc = dev_buf(3, (size_t)(n_windows + 1) * 8, &d_off))) return rc;
         CU(cudaMemcpyAsync(d_off, sample_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, st));
     }
-    CU(cudaMemcpyAsync(d_l, lin, (size_t)n_windows * CPI_LIN_DOUBLES * 8, cudaMemcpyHostToDevice, st));
-    if (entries > 0) CU(cudaMemcpyAsync(d_s, samples, (size_t)entries * CPI_SAMPLE_DOUBLES * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_l, lin, (size_t)n_windows * CPI_LIN_DOUBLES * es, cudaMemcpyHostToDevice, st));
+    if (entries > 0) CU(cudaMemcpyAsync(d_s, samples, (size_t)entries * CPI_SAMPLE_DOUBLES * es, cudaMemcpyHostToDevice, st));
     rc = cpi_preintegrate_batch(model, dtype, n_windows, (const int64_t*)d_off, ns_uniform, d_s, d_l, sigmas, flags, d_o, st);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out_records, d_o, (size_t)n_windows * rd * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_records, d_o, (size_t)n_windows * rd * es, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return CPI_OK;
 }

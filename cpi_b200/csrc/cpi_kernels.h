@@ -9,9 +9,9 @@ struct PreintParams {
     int64_t n_windows;
     const int64_t* offsets;   // device, may be null (uniform windows)
     int64_t ns_uniform;
-    const double* samples;    // device
-    const double* lin;        // device
-    double* out;              // device
+    const void* samples;      // device, double (dtype 64) or float (dtype 32)
+    const void* lin;          // device
+    void* out;                // device
     double q_w, q_wb, q_a, q_ab;   // sigma^2  (CpiBase.h:54-57)
     int wpb;                  // windows per block == shared-memory window stride (chosen by preint_launch)
 };
@@ -28,8 +28,8 @@ struct FactorParams {
     double* H2;
 };
 
-int preint_pick_wpb(int model, int64_t n_windows, int num_sms, int max_smem_bytes);
-cudaError_t preint_launch(int model, int flags, const PreintParams& p0, int num_sms, int max_smem_bytes, cudaStream_t st, int* launches);
+int preint_pick_wpb(int model, int dtype, int64_t n_windows, int num_sms);
+cudaError_t preint_launch(int model, int dtype, int flags, const PreintParams& p0, int num_sms, int max_smem_bytes, cudaStream_t st, int* launches);
 cudaError_t factor_launch(int model, const FactorParams& p, cudaStream_t st);
 cudaError_t predict_launch(int model, int64_t n, const double* states, const double* records, const double* lin, double* out, cudaStream_t st);
 cudaError_t retract_launch(int64_t n, const double* states, const double* xi, double* out, cudaStream_t st);

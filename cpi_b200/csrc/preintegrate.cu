@@ -45,9 +45,7 @@ enum : int {
     // model 2, default mode: the non-trivial blocks of Discrete_J_b in the consumed columns (bg, ba, theta_klin)
     D_TG = 0, D_VG = 9, D_PG = 18, D_VA = 27, D_PA = 36, D_VL = 45, D_PL = 54, ND = 63,
     // analytic Jacobian state (model 1; model 2 with CPI_FLAG_ANALYTIC_JACOBIANS): same 63-double region
-    J_Q = 0, J_A = 9, J_B = 18, H_A = 27, H_B = 36, O_A = 45, O_B = 54,
-    // TMA staging: two buffers of one 128-byte line per window, NOT element-major
-    BUF_DOUBLES = 16
+    J_Q = 0, J_A = 9, J_B = 18, H_A = 27, H_B = 36, O_A = 45, O_B = 54
 };
 
 // Per-model tile description.  S (window stride == max windows per CTA) is a compile-time constant so that every
@@ -58,20 +56,24 @@ enum : int {
 //              soon as the last dependant has run -- see rk4_cascade)
 //   then       Jacobian state (45 / 63 doubles)
 enum : int { SLOT_A = 0, SLOT_B = 27, SLOT_C = 54, SLOT_D = 81 /*18*/, SLOT_E = 99 /*model 2*/ };
-template <int MODEL> struct Tile;
-template <> struct Tile<1> {
-    static constexpr int NSLOT = 99, NJ = 45, S = 80;
-    static constexpr int OFF_PB = NP, OFF_SL = 2 * NP, OFF_J = 2 * NP + NSLOT, ELEMS = 2 * NP + NSLOT + NJ;   // 324
-};
-template <> struct Tile<2> {
-    static constexpr int NSLOT = 126, NJ = ND, S = 72;
-    static constexpr int OFF_PB = NP, OFF_SL = 2 * NP, OFF_J = 2 * NP + NSLOT, ELEMS = 2 * NP + NSLOT + ND;   // 369
-};
-template <int MODEL> __host__ __device__ constexpr size_t tile_bytes() {
-    // element-major part + per-window staging buffers (2 x 16 doubles = two 128-byte lines) + 2 mbarriers
-    return (size_t)Tile<MODEL>::S * (Tile<MODEL>::ELEMS + 2 * BUF_DOUBLES + 2) * sizeof(double);
+template <int MODEL, class T> struct Tile;
+template <> struct Tile<1, double> { static constexpr int NSLOT = 99, NJ = 45, S = 80; };
+template <> struct Tile<2, double> { static constexpr int NSLOT = 126, NJ = ND, S = 72; };
+// fp32 storage (dtype 32): the covariance tile and its stage slots are float, the Jacobian state stays double
+template <> struct Tile<1, float> { static constexpr int NSLOT = 99, NJ = 45, S = 128; };
+template <> struct Tile<2, float> { static constexpr int NSLOT = 126, NJ = ND, S = 112; };
+// byte layout of the dynamic shared memory:  [J: NJ doubles x S] [P a | P b | slots : T x S each element] [2 x 128 B staging per window] [2 mbarriers per window]
+template <int MODEL, class T> __host__ __device__ constexpr size_t tile_off_T() { return (size_t)Tile<MODEL, T>::NJ * Tile<MODEL, T>::S * 8; }
+template <int MODEL, class T> __host__ __device__ constexpr size_t tile_off_buf() {
+    return tile_off_T<MODEL, T>() + (size_t)(2 * NP + Tile<MODEL, T>::NSLOT) * Tile<MODEL, T>::S * sizeof(T);
 }
-static_assert(tile_bytes<1>() <= 232448 && tile_bytes<2>() <= 232448, "tile exceeds 227 KB");
+template <int MODEL, class T> __host__ __device__ constexpr size_t tile_off_bar() { return tile_off_buf<MODEL, T>() + (size_t)Tile<MODEL, T>::S * 256; }
+template <int MODEL, class T> __host__ __device__ constexpr size_t tile_bytes() { return tile_off_bar<MODEL, T>() + (size_t)Tile<MODEL, T>::S * 16; }
+static_assert(tile_bytes<1, double>() <= 232448 && tile_bytes<2, double>() <= 232448 && tile_bytes<1, float>() <= 232448 &&
+              tile_bytes<2, float>() <= 232448, "tile exceeds 227 KB");
+static_assert(tile_off_T<1, float>() % 16 == 0 && tile_off_T<2, float>() % 16 == 0 && tile_off_buf<1, float>() % 16 == 0 &&
+              tile_off_buf<2, float>() % 16 == 0 && tile_off_buf<1, double>() % 16 == 0 && tile_off_buf<2, double>() % 16 == 0,
+              "cp.async.bulk destinations must be 16-byte aligned");
 
 // ---- TMA (1-D bulk copy) + mbarrier primitives: SASS UBLKCP / SYNCS ---------------------------------------------------
 CPI_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -94,12 +96,12 @@ CPI_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;"
 // ---- block loaders ----------------------------------------------------------------------------------------------------
 #define SM(buf, idx) (buf)[(idx) * S]
 
-template <int S> CPI_DEV void ld9(const double* b, int off, double* x) {
+template <int S, class TP, class TX> CPI_DEV void ld9(const TP* b, int off, TX* x) {
 #pragma unroll
     for (int k = 0; k < 9; k++) x[k] = SM(b, off + k);
 }
-template <int S> CPI_DEV void ldsym(const double* b, int off, double* x) {   // packed sym -> full row-major 3x3
-    const double a0 = SM(b, off), a1 = SM(b, off + 1), a2 = SM(b, off + 2), a3 = SM(b, off + 3), a4 = SM(b, off + 4), a5 = SM(b, off + 5);
+template <int S, class TP, class TX> CPI_DEV void ldsym(const TP* b, int off, TX* x) {   // packed sym -> full row-major 3x3
+    const TX a0 = SM(b, off), a1 = SM(b, off + 1), a2 = SM(b, off + 2), a3 = SM(b, off + 3), a4 = SM(b, off + 4), a5 = SM(b, off + 5);
     x[0] = a0; x[1] = a1; x[2] = a2; x[3] = a1; x[4] = a3; x[5] = a4; x[6] = a2; x[7] = a4; x[8] = a5;
 }
 
@@ -118,29 +120,29 @@ template <int S> CPI_DEV void ldsym(const double* b, int off, double* x) {   // 
 #define CPI_SECTION() asm volatile("" ::: "memory")
 #define CN(s) ((s) < 2 ? hdt : dt)                       /* x_{s+2} = x_1 + CN(s) k_{s+1}:  dt/2, dt/2, dt   (CpiV1.h:312, 323, 344) */
 #define RS(s) ((s) == 0 ? R : ((s) == 3 ? R1 : Rm))       /* F evaluated at R_old, R_mid, R_mid, R_new */
-#define KSUM(ks, k, s) ((s) == 0 ? (k) : ((s) == 3 ? (ks) + (k) : fma(2.0, (k), (ks))))   /* ((k1 + 2 k2) + 2 k3) + k4  (CpiV1.h:352) */
+#define KSUM(ks, k, s) ((s) == 0 ? (k) : ((s) == 3 ? (ks) + (k) : fma(T(2), (k), (ks))))   /* ((k1 + 2 k2) + 2 k3) + k4  (CpiV1.h:352) */
 
-template <int S> CPI_DEV void st9(double* b, int off, const double* x) {
+template <int S, class TP, class TX> CPI_DEV void st9(TP* b, int off, const TX* x) {
 #pragma unroll
     for (int e = 0; e < 9; e++) SM(b, off + e) = x[e];
 }
-template <int S> CPI_DEV void ldst9(const double* Po, int off, const double* sl, int slot, int s, double* x) {
+template <int S, class T> CPI_DEV void ldst9(const T* Po, int off, const T* sl, int slot, int s, T* x) {
     if (s == 0) ld9<S>(Po, off, x); else ld9<S>(sl, slot + (s - 1) * 9, x);
 }
-template <int S> CPI_DEV void ldstsym(const double* Po, int off, const double* sl, int slot, int s, double* x) {
+template <int S, class T> CPI_DEV void ldstsym(const T* Po, int off, const T* sl, int slot, int s, T* x) {
     if (s == 0) ldsym<S>(Po, off, x); else ldsym<S>(sl, slot + (s - 1) * 6, x);
 }
-CPI_DEV void sym_expand(const double* a, double* x) { x[0] = a[0]; x[1] = a[1]; x[2] = a[2]; x[3] = a[1]; x[4] = a[3]; x[5] = a[4]; x[6] = a[2]; x[7] = a[4]; x[8] = a[5]; }
+template <class T> CPI_DEV void sym_expand(const T* a, T* x) { x[0] = a[0]; x[1] = a[1]; x[2] = a[2]; x[3] = a[1]; x[4] = a[3]; x[5] = a[4]; x[6] = a[2]; x[7] = a[4]; x[8] = a[5]; }
 
 // rows of  -R^T [a x] : row i = a cross r_i  with r_i = column i of R (R row-major)
-CPI_DEV void make_A(const double* R, const double* a, double* A) {
+template <class T> CPI_DEV void make_A(const T* R, const T* a, T* A) {
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        const double r[3] = {R[i], R[3 + i], R[6 + i]};
+        const T r[3] = {R[i], R[3 + i], R[6 + i]};
         cross(a, r, &A[3 * i]);
     }
 }
-CPI_DEV void make_B(const double* R, double* B) {   // -R^T
+template <class T> CPI_DEV void make_B(const T* R, T* B) {   // -R^T
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -148,29 +150,36 @@ CPI_DEV void make_B(const double* R, double* B) {   // -R^T
 }
 
 
-template <int MODEL, int S>
-CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double* w, const double* ah, const double* gt,
-                         const double* R, const double* Rm, const double* R1, double pgg, double paa, double dt,
-                         double q_w, double q_wb, double q_a, double q_ab) {
-    const double hdt = dt * 0.5, dt6 = dt / 6.0;
+template <int MODEL, int S, class T>
+CPI_DEV void rk4_cascade(const T* Po, T* Pn, T* sl, const double* w_, const double* ah_, const double* gt_,
+                         const double* R_, const double* Rm_, const double* R1_, double pgg_, double paa_, double dt_,
+                         double q_w_, double q_wb_, double q_a_, double q_ab_) {
+    // operands in the tile's arithmetic type (no-op copies for T = double)
+    T w[3], ah[3], gt[3], R[9], Rm[9], R1[9];
+#pragma unroll
+    for (int e = 0; e < 3; e++) { w[e] = (T)w_[e]; ah[e] = (T)ah_[e]; gt[e] = (T)gt_[e]; }
+#pragma unroll
+    for (int e = 0; e < 9; e++) { R[e] = (T)R_[e]; Rm[e] = (T)Rm_[e]; R1[e] = (T)R1_[e]; }
+    const T pgg = (T)pgg_, paa = (T)paa_, dt = (T)dt_, q_w = (T)q_w_, q_wb = (T)q_wb_, q_a = (T)q_a_, q_ab = (T)q_ab_;
+    const T hdt = dt * T(0.5), dt6 = (T)(dt_ / 6.0);
     constexpr int SL_TG = SLOT_A, SL_TT = SLOT_B, SL_VG = SLOT_C, SL_CT = SLOT_A, SL_CV = SLOT_B, SL_VA = SLOT_C, SL_VV = SLOT_D;
     constexpr int SL_VT = (MODEL == 1) ? SLOT_A : SLOT_E, SL_PT = (MODEL == 1) ? SLOT_B : SLOT_A, SL_PV = (MODEL == 1) ? SLOT_A : SLOT_E;
 
     {   // ---- tg:  k = -W x - pgg_s I        (-W c = c cross w, column-wise)
-        double x1[9], x[9], ks[9], k[9];
+        T x1[9], x[9], ks[9], k[9];
         ld9<S>(Po, TG, x1);
 #pragma unroll
         for (int e = 0; e < 9; e++) x[e] = x1[e];
 #pragma unroll
         for (int s = 0; s < 4; s++) {
-            const double pg_s = (s == 0) ? pgg : fma(q_wb, (s == 3 ? dt : hdt), pgg);
+            const T pg_s = (s == 0) ? pgg : fma(q_wb, (s == 3 ? dt : hdt), pgg);
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-                const double col[3] = {x[j], x[3 + j], x[6 + j]};
-                double c3[3];
+                const T col[3] = {x[j], x[3 + j], x[6 + j]};
+                T c3[3];
                 cross(col, w, c3);
 #pragma unroll
-                for (int i = 0; i < 3; i++) k[3 * i + j] = c3[i] - (i == j ? pg_s : 0.0);
+                for (int i = 0; i < 3; i++) k[3 * i + j] = c3[i] - (i == j ? pg_s : T(0));
             }
 #pragma unroll
             for (int e = 0; e < 9; e++) ks[e] = KSUM(ks[e], k[e], s);
@@ -185,7 +194,7 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
     }
     CPI_SECTION();
     {   // ---- tt:  k = M + M^T + q_w I,  M = -W x - P_tg^T
-        double a1[6], a[6], ks[6], x[9], M[9], tg[9];
+        T a1[6], a[6], ks[6], x[9], M[9], tg[9];
 #pragma unroll
         for (int e = 0; e < 6; e++) a[e] = a1[e] = SM(Po, TT + e);
 #pragma unroll
@@ -194,8 +203,8 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
             ldst9<S>(Po, TG, sl, SL_TG, s, tg);
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-                const double col[3] = {x[j], x[3 + j], x[6 + j]};
-                double c3[3];
+                const T col[3] = {x[j], x[3 + j], x[6 + j]};
+                T c3[3];
                 cross(col, w, c3);
 #pragma unroll
                 for (int i = 0; i < 3; i++) M[3 * i + j] = c3[i] - tg[3 * j + i];
@@ -204,7 +213,7 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
             for (int i = 0; i < 3; i++)
 #pragma unroll
                 for (int j = i; j < 3; j++) {
-                    const double kk = M[3 * i + j] + M[3 * j + i] + (i == j ? q_w : 0.0);
+                    const T kk = M[3 * i + j] + M[3 * j + i] + (i == j ? q_w : T(0));
                     ks[sym3(i, j)] = KSUM(ks[sym3(i, j)], kk, s);
                     if (s < 3) { a[sym3(i, j)] = fma(kk, CN(s), a1[sym3(i, j)]); SM(sl, SL_TT + s * 6 + sym3(i, j)) = a[sym3(i, j)]; }
                 }
@@ -214,7 +223,7 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
     }
     CPI_SECTION();
     {   // ---- vg:  k = A_s P_tg,s (+ C_s P_cg, P_cg = P_tg at step start)    and pg:  k = P_vg,s  (pure integral of vg's stage values)
-        double x1[9], x[9], ks[9], k[9], pg1[9], pgs[9], tg[9], A[9], C[9], cg[9];
+        T x1[9], x[9], ks[9], k[9], pg1[9], pgs[9], tg[9], A[9], C[9], cg[9];
         ld9<S>(Po, VG, x1); ld9<S>(Po, PG, pg1);
         if (MODEL == 2) ld9<S>(Po, TG, cg);
 #pragma unroll
@@ -227,7 +236,7 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
             for (int i = 0; i < 3; i++)
 #pragma unroll
                 for (int j = 0; j < 3; j++) {
-                    double t = 0.0;
+                    T t = T(0);
 #pragma unroll
                     for (int m = 0; m < 3; m++) t = fma(A[3 * i + m], tg[3 * m + j], t);
                     if (MODEL == 2) {
@@ -250,16 +259,16 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
     CPI_SECTION();
     if (MODEL == 2) {
         // ---- ct (transient clone rows x theta; starts as P_tt, CpiV2.h:436-441):  k = x W - P_cg ;  only its stage values matter
-        double x1[9], x[9], cg[9];
+        T x1[9], x[9], cg[9];
         ldsym<S>(Po, TT, x1); ld9<S>(Po, TG, cg);
 #pragma unroll
         for (int e = 0; e < 9; e++) x[e] = x1[e];
 #pragma unroll
         for (int s = 0; s < 3; s++) {
-            double k[9];
+            T k[9];
 #pragma unroll
             for (int i = 0; i < 3; i++) {
-                double c3[3];
+                T c3[3];
                 cross(&x[3 * i], w, c3);
 #pragma unroll
                 for (int j = 0; j < 3; j++) k[3 * i + j] = c3[j] - cg[3 * i + j];
@@ -271,7 +280,7 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
         CPI_SECTION();
     }
     {   // ---- vt:  k = A_s P_tt,s + x W - P_vg,s (+ C_s P_ct,s)
-        double x1[9], x[9], ks[9], k[9], tt[9], vg[9], A[9], C[9], ct[9];
+        T x1[9], x[9], ks[9], k[9], tt[9], vg[9], A[9], C[9], ct[9];
         ld9<S>(Po, VT, x1);
 #pragma unroll
         for (int e = 0; e < 9; e++) x[e] = x1[e];
@@ -283,11 +292,11 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
             if (MODEL == 2) { if (s == 0) ldsym<S>(Po, TT, ct); else ld9<S>(sl, SL_CT + (s - 1) * 9, ct); }
 #pragma unroll
             for (int i = 0; i < 3; i++) {
-                double c3[3];
+                T c3[3];
                 cross(&x[3 * i], w, c3);
 #pragma unroll
                 for (int j = 0; j < 3; j++) {
-                    double t = c3[j] - vg[3 * i + j];
+                    T t = c3[j] - vg[3 * i + j];
 #pragma unroll
                     for (int m = 0; m < 3; m++) t = fma(A[3 * i + m], tt[3 * m + j], t);
                     if (MODEL == 2) {
@@ -311,7 +320,7 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
     CPI_SECTION();
     if (MODEL == 2) {
         // ---- cv (transient; starts as P_theta,v = P_vt^T):  k = P_ct,s A_s^T + P_cc C_s^T,  P_cc = P_tt at step start
-        double x1[9], cc[9], A[9], C[9];
+        T x1[9], cc[9], A[9], C[9];
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -319,14 +328,14 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
         ldsym<S>(Po, TT, cc);
 #pragma unroll
         for (int s = 0; s < 3; s++) {
-            double ct[9], x[9];
+            T ct[9], x[9];
             if (s != 2) { make_A(RS(s), ah, A); make_A(RS(s), gt, C); }
             if (s == 0) ldsym<S>(Po, TT, ct); else ld9<S>(sl, SL_CT + (s - 1) * 9, ct);
 #pragma unroll
             for (int i = 0; i < 3; i++)
 #pragma unroll
                 for (int j = 0; j < 3; j++) {
-                    double t = 0.0;
+                    T t = T(0);
 #pragma unroll
                     for (int m = 0; m < 3; m++) t = fma(ct[3 * i + m], A[3 * j + m], t);
 #pragma unroll
@@ -338,7 +347,7 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
         CPI_SECTION();
     }
     {   // ---- pt:  k = P_vt,s + x W - P_pg,s ;  P_pg,s = P_pg + CN(s-1) P_vg,s-1  (recomputed, not stored)
-        double x1[9], x[9], ks[9], k[9], vt[9], pg1[9], pg[9], vgp[9];
+        T x1[9], x[9], ks[9], k[9], vt[9], pg1[9], pg[9], vgp[9];
         ld9<S>(Po, PT, x1); ld9<S>(Po, PG, pg1);
 #pragma unroll
         for (int e = 0; e < 9; e++) { x[e] = x1[e]; pg[e] = pg1[e]; }
@@ -352,7 +361,7 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
             }
 #pragma unroll
             for (int i = 0; i < 3; i++) {
-                double c3[3];
+                T c3[3];
                 cross(&x[3 * i], w, c3);
 #pragma unroll
                 for (int j = 0; j < 3; j++) k[3 * i + j] = vt[3 * i + j] + c3[j] - pg[3 * i + j];
@@ -370,17 +379,17 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
     }
     CPI_SECTION();
     {   // ---- va:  k = paa_s B_s      and pa:  k = P_va,s
-        double x1[9], x[9], ks[9], pa1[9], pas[9], B[9];
+        T x1[9], x[9], ks[9], pa1[9], pas[9], B[9];
         ld9<S>(Po, VA, x1); ld9<S>(Po, PA, pa1);
 #pragma unroll
         for (int e = 0; e < 9; e++) x[e] = x1[e];
 #pragma unroll
         for (int s = 0; s < 4; s++) {
-            const double pa_s = (s == 0) ? paa : fma(q_ab, (s == 3 ? dt : hdt), paa);
+            const T pa_s = (s == 0) ? paa : fma(q_ab, (s == 3 ? dt : hdt), paa);
             if (s != 2) make_B(RS(s), B);
 #pragma unroll
             for (int e = 0; e < 9; e++) {
-                const double kk = pa_s * B[e];
+                const T kk = pa_s * B[e];
                 ks[e] = KSUM(ks[e], kk, s);
                 pas[e] = KSUM(pas[e], x[e], s);
                 if (s < 3) x[e] = fma(kk, CN(s), x1[e]);
@@ -393,13 +402,13 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
     CPI_SECTION();
     {   // ---- vv:  k = M + M^T + q_a I,  M = A_s P_vt,s^T + B_s P_va,s^T (+ C_s P_cv,s),  B_s = -R_s^T used straight from R_s.
         //      Terms are accumulated in fenced passes so that only one operand pair is live at a time.
-        double a1[6], ks[6], M[9];
+        T a1[6], ks[6], M[9];
 #pragma unroll
         for (int e = 0; e < 6; e++) a1[e] = SM(Po, VV + e);
 #pragma unroll
         for (int s = 0; s < 4; s++) {
             {
-                double A[9], vt[9];
+                T A[9], vt[9];
                 make_A(RS(s), ah, A);
                 ldst9<S>(Po, VT, sl, SL_VT, s, vt);
 #pragma unroll
@@ -409,8 +418,8 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
             }
             CPI_SECTION();
             {
-                double va[9];
-                const double* Rs = RS(s);
+                T va[9];
+                const T* Rs = RS(s);
                 ldst9<S>(Po, VA, sl, SL_VA, s, va);
 #pragma unroll
                 for (int i = 0; i < 3; i++)
@@ -421,7 +430,7 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
             }
             if (MODEL == 2) {
                 CPI_SECTION();
-                double C[9], cv[9];
+                T C[9], cv[9];
                 make_A(RS(s), gt, C);
                 if (s == 0) {
 #pragma unroll
@@ -440,7 +449,7 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
             for (int i = 0; i < 3; i++)
 #pragma unroll
                 for (int j = i; j < 3; j++) {
-                    const double kk = M[3 * i + j] + M[3 * j + i] + (i == j ? q_a : 0.0);
+                    const T kk = M[3 * i + j] + M[3 * j + i] + (i == j ? q_a : T(0));
                     ks[sym3(i, j)] = KSUM(ks[sym3(i, j)], kk, s);
                     if (s < 3) SM(sl, SL_VV + s * 6 + sym3(i, j)) = fma(kk, CN(s), a1[sym3(i, j)]);
                 }
@@ -452,12 +461,12 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
     CPI_SECTION();
     {   // ---- pv:  k = P_vv,s + P_pt,s A_s^T + P_pa,s B_s^T (+ P_cp,s^T C_s^T);  P_pa,s = P_pa + CN(s-1) P_va,s-1 and
         //      P_cp,s = P_pt^T + CN(s-1) P_cv,s-1 are recomputed from the va / cv stage values instead of being stored
-        double x1[9], ks[9], k[9];
+        T x1[9], ks[9], k[9];
         ld9<S>(Po, PV, x1);
 #pragma unroll
         for (int s = 0; s < 4; s++) {
             {
-                double A[9], pt[9];
+                T A[9], pt[9];
                 ldstsym<S>(Po, VV, sl, SL_VV, s, k);
                 make_A(RS(s), ah, A);
                 ldst9<S>(Po, PT, sl, SL_PT, s, pt);
@@ -470,11 +479,11 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
             }
             CPI_SECTION();
             {
-                double pa[9];
-                const double* Rs = RS(s);
+                T pa[9];
+                const T* Rs = RS(s);
                 ld9<S>(Po, PA, pa);
                 if (s > 0) {
-                    double prev[9];
+                    T prev[9];
                     ldst9<S>(Po, VA, sl, SL_VA, s - 1, prev);
 #pragma unroll
                     for (int e = 0; e < 9; e++) pa[e] = fma(prev[e], CN(s - 1), pa[e]);
@@ -488,14 +497,14 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
             }
             if (MODEL == 2) {
                 CPI_SECTION();
-                double C[9], cp[9];
+                T C[9], cp[9];
                 make_A(RS(s), gt, C);
 #pragma unroll
                 for (int i = 0; i < 3; i++)
 #pragma unroll
                     for (int j = 0; j < 3; j++) cp[3 * i + j] = SM(Po, PT + 3 * j + i);     // P_theta,p = P_pt^T
                 if (s > 0) {
-                    double prev[9];
+                    T prev[9];
                     if (s == 1) {
 #pragma unroll
                         for (int i = 0; i < 3; i++)
@@ -524,7 +533,7 @@ CPI_DEV void rk4_cascade(const double* Po, double* Pn, double* sl, const double*
     }
     CPI_SECTION();
     {   // ---- pp:  k = P_pv,s + P_pv,s^T
-        double a1[6], ks[6], pv[9];
+        T a1[6], ks[6], pv[9];
 #pragma unroll
         for (int e = 0; e < 6; e++) a1[e] = SM(Po, PP + e);
 #pragma unroll
@@ -561,28 +570,31 @@ CPI_DEV void rot_apply(double a, double b, const double* w, const double* R, dou
 // two samples (112 B, fetched as ONE aligned 128-byte transaction that also covers the 8-byte misalignment of odd
 // window offsets) in flight ahead of the arithmetic.  The last chunk of a window is read with plain loads because the
 // aligned 128-byte fetch could run past the end of the caller's buffer there.
-template <int MODEL, bool AVG, bool ANALYTIC>
-__global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
-    using T = Tile<MODEL>;
-    constexpr int S = T::S;
-    extern __shared__ __align__(128) double smem[];
+template <int MODEL, bool AVG, bool ANALYTIC, class T>
+__global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
+    using TL = Tile<MODEL, T>;
+    constexpr int S = TL::S;
+    constexpr int EPL = 16 / (int)sizeof(T);             // elements per 16 bytes
+    constexpr int CH = 8 / (int)sizeof(T) * 2;           // samples per TMA chunk: 2 (fp64, 2 x 56 B) or 4 (fp32, 4 x 28 B) = 112 B
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int64_t win = (int64_t)blockIdx.x * p.wpb + tid;
     if (tid >= p.wpb || win >= p.n_windows) return;
 
-    double* P = smem + tid;                                       // current covariance tile (ping-pongs with Pn every step)
-    double* Pn = P + (size_t)T::OFF_PB * S;
-    double* sl = smem + tid + (size_t)T::OFF_SL * S;              // RK4 stage-value slots
-    double* Jt = smem + tid + (size_t)T::OFF_J * S;               // analytic Jacobians, or Discrete_J_b blocks (model 2 default)
-    double* buf = smem + (size_t)T::ELEMS * S + (size_t)tid * (2 * BUF_DOUBLES);
-    const uint32_t bar0 = smem_u32(smem + (size_t)(T::ELEMS + 2 * BUF_DOUBLES) * S + 2 * tid);
+    double* Jt = reinterpret_cast<double*>(smem_raw) + tid;                       // analytic Jacobians, or Discrete_J_b blocks (model 2 default)
+    T* P = reinterpret_cast<T*>(smem_raw + tile_off_T<MODEL, T>()) + tid;         // current covariance tile (ping-pongs with Pn every step)
+    T* Pn = P + (size_t)NP * S;
+    T* sl = P + (size_t)2 * NP * S;                                               // RK4 stage-value slots
+    const T* buf = reinterpret_cast<const T*>(smem_raw + tile_off_buf<MODEL, T>() + (size_t)tid * 256);
+    const uint32_t buf0 = smem_u32(buf);
+    const uint32_t bar0 = smem_u32(smem_raw + tile_off_bar<MODEL, T>() + (size_t)tid * 16);
 
     // ---- per-window constants (setLinearizationPoints, CpiBase.h:73-80)
-    const double* lin = p.lin + win * CPI_LIN_DOUBLES;
-    const double bw[3] = {lin[0], lin[1], lin[2]}, ba[3] = {lin[3], lin[4], lin[5]};
+    const T* lin = reinterpret_cast<const T*>(p.lin) + win * CPI_LIN_DOUBLES;
+    const double bw[3] = {(double)lin[0], (double)lin[1], (double)lin[2]}, ba[3] = {(double)lin[3], (double)lin[4], (double)lin[5]};
     double g_k[3] = {0, 0, 0};
     if (MODEL == 2) {
-        const double q[4] = {lin[6], lin[7], lin[8], lin[9]}, g[3] = {lin[10], lin[11], lin[12]};
+        const double q[4] = {(double)lin[6], (double)lin[7], (double)lin[8], (double)lin[9]}, g[3] = {(double)lin[10], (double)lin[11], (double)lin[12]};
         double RG[9];
         quat_2_Rot(q, RG);
         mv33(RG, g, g_k);                                // quat_2_Rot(q_k_lin) * grav   (CpiV2.h:99, 202, 315)
@@ -591,11 +603,11 @@ __global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
     if (p.offsets) { o0 = p.offsets[win]; nsteps = p.offsets[win + 1] - o0 - (AVG ? 1 : 0); }
     else { o0 = win * (p.ns_uniform + (AVG ? 1 : 0)); nsteps = p.ns_uniform; }
     if (nsteps < 0) nsteps = 0;
-    const double* sp = p.samples + o0 * CPI_SAMPLE_DOUBLES;
+    const T* sp = reinterpret_cast<const T*>(p.samples) + o0 * CPI_SAMPLE_DOUBLES;
 
     // ---- TMA pipeline set-up
-    const int shift = (int)(o0 & 1);                     // 56*o0 bytes is 16-byte aligned iff o0 is even
-    const int64_t n_tma = AVG ? 0 : (nsteps > 0 ? (nsteps - 1) / 2 : 0);   // chunks with at least one more sample after them
+    const int shift = (int)((7 * o0) % EPL);             // misalignment of the window start w.r.t. 16 bytes, in elements
+    const int64_t n_tma = AVG ? 0 : (nsteps > 0 ? (nsteps - 1) / CH : 0);   // chunks with at least one more sample after them
     if (!AVG) {
         mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -604,7 +616,7 @@ __global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
         for (int c = 0; c < 2; c++)
             if (c < n_tma) {
                 mbar_arrive_expect_tx(bar0 + 8 * c, 128);
-                bulk_g2s(smem_u32(buf + c * BUF_DOUBLES), sp + 14 * c - shift, 128, bar0 + 8 * c);
+                bulk_g2s(buf0 + 128 * c, sp + 7 * CH * c - shift, 128, bar0 + 8 * c);
             }
     }
 
@@ -613,32 +625,32 @@ __global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
     double alpha[3] = {0, 0, 0}, beta[3] = {0, 0, 0}, DT = 0.0;
     double pgg = 0.0, paa = 0.0;
 #pragma unroll 1
-    for (int e = 0; e < NP; e++) SM(P, e) = 0.0;
+    for (int e = 0; e < NP; e++) SM(P, e) = T(0);
 #pragma unroll 1
-    for (int e = 0; e < T::NJ; e++) SM(Jt, e) = 0.0;
+    for (int e = 0; e < TL::NJ; e++) SM(Jt, e) = 0.0;
 
 #pragma unroll 1
     for (int64_t it = 0; it < nsteps; it++) {
         // ---- fetch entry `it` (and, for imu_avg, the (w, a) of entry it+1)
         double s0[7], nx[6];
-        if (!AVG && it < 2 * n_tma) {
-            const int64_t c = it >> 1;
-            const int b = (int)(c & 1), j = (int)(it & 1);
+        if (!AVG && it < CH * n_tma) {
+            const int64_t c = it / CH;
+            const int b = (int)(c & 1), j = (int)(it % CH);
             if (j == 0) mbar_wait(bar0 + 8 * b, (uint32_t)((c >> 1) & 1));
-            const double* src = buf + b * BUF_DOUBLES + shift + 7 * j;
+            const T* src = buf + b * (128 / (int)sizeof(T)) + shift + 7 * j;
 #pragma unroll
-            for (int e = 0; e < 7; e++) s0[e] = src[e];
-            if (j == 1 && c + 2 < n_tma) {
+            for (int e = 0; e < 7; e++) s0[e] = (double)src[e];
+            if (j == CH - 1 && c + 2 < n_tma) {
                 fence_proxy_async();                     // generic-proxy reads of this buffer are done; hand it to the async proxy
                 mbar_arrive_expect_tx(bar0 + 8 * b, 128);
-                bulk_g2s(smem_u32(buf + b * BUF_DOUBLES), sp + 14 * (c + 2) - shift, 128, bar0 + 8 * b);
+                bulk_g2s(buf0 + 128 * b, sp + 7 * CH * (c + 2) - shift, 128, bar0 + 8 * b);
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < 7; e++) s0[e] = __ldg(sp + it * CPI_SAMPLE_DOUBLES + e);
+            for (int e = 0; e < 7; e++) s0[e] = (double)__ldg(sp + it * CPI_SAMPLE_DOUBLES + e);
             if (AVG) {
 #pragma unroll
-                for (int e = 0; e < 6; e++) nx[e] = __ldg(sp + (it + 1) * CPI_SAMPLE_DOUBLES + e);
+                for (int e = 0; e < 6; e++) nx[e] = (double)__ldg(sp + (it + 1) * CPI_SAMPLE_DOUBLES + e);
             }
         }
         const double dt = s0[6];
@@ -817,8 +829,8 @@ __global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
 
         // ---- covariance: the reference's RK4, block-serial on the block-triangular Lyapunov operator (rk4_cascade)
         const double hdt = dt * 0.5, dt6 = dt / 6.0;
-        rk4_cascade<MODEL, S>(P, Pn, sl, wh, ah, g_tau, R, Rm, R1, pgg, paa, dt, p.q_w, p.q_wb, p.q_a, p.q_ab);
-        { double* t = P; P = Pn; Pn = t; }
+        rk4_cascade<MODEL, S, T>(P, Pn, sl, wh, ah, g_tau, R, Rm, R1, pgg, paa, dt, p.q_w, p.q_wb, p.q_a, p.q_ab);
+        { T* t = P; P = Pn; Pn = t; }
         pgg += dt6 * (p.q_wb + 2.0 * p.q_wb + 2.0 * p.q_wb + p.q_wb);
         paa += dt6 * (p.q_ab + 2.0 * p.q_ab + 2.0 * p.q_ab + p.q_ab);
 
@@ -858,8 +870,8 @@ __global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
                         for (int e = 0; e < 9; e++) {
                             xtt[e] = ((e % 4 == 0) ? 1.0 : 0.0) + k1[e] * cstep;
                             xtg[e] = k2[e] * cstep;
-                            SM(sl, SLOT_A + st * 9 + e) = xtt[e];
-                            SM(sl, SLOT_B + st * 9 + e) = xtg[e];
+                            SM(sl, SLOT_A + st * 9 + e) = (T)xtt[e];
+                            SM(sl, SLOT_B + st * 9 + e) = (T)xtg[e];
                         }
                     }
                 }
@@ -869,7 +881,7 @@ __global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
                 for (int e = 0; e < 9; e++) { stt[e] = ((e % 4 == 0) ? 1.0 : 0.0) + dt6 * stt[e]; stg[e] = dt6 * stg[e]; }   // Phi_tt, Phi_tg
                 mul33(stt, Dtg, n1);
 #pragma unroll
-                for (int e = 0; e < 9; e++) SM(sl, SLOT_C + e) = n1[e] + stg[e];
+                for (int e = 0; e < 9; e++) SM(sl, SLOT_C + e) = (T)(n1[e] + stg[e]);
             }
             CPI_SECTION();
             {   // section 2: bg column of rows v and p
@@ -947,7 +959,7 @@ __global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
                     }
                 // commit D_tg' (parked in slot C by section 1; sections 2 needed the old value)
 #pragma unroll
-                for (int e = 0; e < 9; e++) SM(Jt, D_TG + e) = SM(sl, SLOT_C + e);
+                for (int e = 0; e < 9; e++) SM(Jt, D_TG + e) = (double)SM(sl, SLOT_C + e);
             }
             CPI_SECTION();
         }
@@ -959,11 +971,11 @@ __global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
 
     // ---- write the record (column-major 3x3 / 15x15, include/cpi_b200.h)
     constexpr int RD = (MODEL == 1) ? CPI_REC_V1_DOUBLES : CPI_REC_V2_DOUBLES;
-    double* rec = p.out + win * (int64_t)RD;
+    T* rec = reinterpret_cast<T*>(p.out) + win * (int64_t)RD;
     {
         double q[4];
         rot_2_quat(R, q);                                  // CpiV1.h:358 (only the last one is ever consumed)
-        rec[CPI_REC_Q] = q[0]; rec[CPI_REC_Q + 1] = q[1]; rec[CPI_REC_Q + 2] = q[2]; rec[CPI_REC_Q + 3] = q[3];
+        rec[CPI_REC_Q] = (T)q[0]; rec[CPI_REC_Q + 1] = (T)q[1]; rec[CPI_REC_Q + 2] = (T)q[2]; rec[CPI_REC_Q + 3] = (T)q[3];
     }
     {
         // Jacobian blocks: analytic state, or the read-out of Discrete_J_b (CpiV2.h:450-458: J_q = -D[theta,bg], J_a = D[p,bg],
@@ -975,30 +987,30 @@ __global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
         for (int i = 0; i < 3; i++)
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-                rec[CPI_REC_R + i + 3 * j] = R[3 * i + j];
-                rec[CPI_REC_JQ + i + 3 * j] = DJ ? -SM(Jt, oJq + 3 * i + j) : SM(Jt, oJq + 3 * i + j);
-                rec[CPI_REC_JA + i + 3 * j] = SM(Jt, oJa + 3 * i + j);
-                rec[CPI_REC_JB + i + 3 * j] = SM(Jt, oJb + 3 * i + j);
-                rec[CPI_REC_HA + i + 3 * j] = SM(Jt, oHa + 3 * i + j);
-                rec[CPI_REC_HB + i + 3 * j] = SM(Jt, oHb + 3 * i + j);
-                if (MODEL == 2) { rec[CPI_REC_OA + i + 3 * j] = SM(Jt, oOa + 3 * i + j); rec[CPI_REC_OB + i + 3 * j] = SM(Jt, oOb + 3 * i + j); }
+                rec[CPI_REC_R + i + 3 * j] = (T)(R[3 * i + j]);
+                rec[CPI_REC_JQ + i + 3 * j] = (T)(DJ ? -SM(Jt, oJq + 3 * i + j) : SM(Jt, oJq + 3 * i + j));
+                rec[CPI_REC_JA + i + 3 * j] = (T)(SM(Jt, oJa + 3 * i + j));
+                rec[CPI_REC_JB + i + 3 * j] = (T)(SM(Jt, oJb + 3 * i + j));
+                rec[CPI_REC_HA + i + 3 * j] = (T)(SM(Jt, oHa + 3 * i + j));
+                rec[CPI_REC_HB + i + 3 * j] = (T)(SM(Jt, oHb + 3 * i + j));
+                if (MODEL == 2) { rec[CPI_REC_OA + i + 3 * j] = (T)(SM(Jt, oOa + 3 * i + j)); rec[CPI_REC_OB + i + 3 * j] = (T)(SM(Jt, oOb + 3 * i + j)); }
             }
     }
 #pragma unroll
-    for (int e = 0; e < 3; e++) { rec[CPI_REC_ALPHA + e] = alpha[e]; rec[CPI_REC_BETA + e] = beta[e]; }
-    rec[CPI_REC_DT] = DT;
+    for (int e = 0; e < 3; e++) { rec[CPI_REC_ALPHA + e] = (T)alpha[e]; rec[CPI_REC_BETA + e] = (T)beta[e]; }
+    rec[CPI_REC_DT] = (T)DT;
     // P_meas, full 15x15: block (I,J), I,J in {theta=0,bg=1,v=2,ba=3,p=4}
-    double* Pm = rec + CPI_REC_P;
-    auto put = [&](int r, int c, double v) { Pm[r + 15 * c] = v; };
+    T* Pm = rec + CPI_REC_P;
+    auto put = [&](int r, int c, T v) { Pm[r + 15 * c] = v; };
 #pragma unroll 1
     for (int i = 0; i < 3; i++)
 #pragma unroll 1
         for (int j = 0; j < 3; j++) {
             const int sidx = sym3(i, j);
             put(i, j, SM(P, TT + sidx));            put(6 + i, 6 + j, SM(P, VV + sidx));      put(12 + i, 12 + j, SM(P, PP + sidx));
-            put(3 + i, 3 + j, i == j ? pgg : 0.0);  put(9 + i, 9 + j, i == j ? paa : 0.0);
-            put(i, 9 + j, 0.0); put(9 + j, i, 0.0); put(3 + i, 9 + j, 0.0); put(9 + j, 3 + i, 0.0);
-            double v;
+            put(3 + i, 3 + j, i == j ? (T)pgg : T(0));  put(9 + i, 9 + j, i == j ? (T)paa : T(0));
+            put(i, 9 + j, T(0)); put(9 + j, i, T(0)); put(3 + i, 9 + j, T(0)); put(9 + j, 3 + i, T(0));
+            T v;
             v = SM(P, TG + 3 * i + j); put(i, 3 + j, v);      put(3 + j, i, v);
             v = SM(P, VT + 3 * i + j); put(6 + i, j, v);      put(j, 6 + i, v);
             v = SM(P, VG + 3 * i + j); put(6 + i, 3 + j, v);  put(3 + j, 6 + i, v);
@@ -1011,44 +1023,47 @@ __global__ void __launch_bounds__(96, 1) k_preintegrate(const PreintParams p) {
 }
 
 // ---- host-side launcher (called from capi.cu) --------------------------------------------------------------------------
-template <int MODEL, bool AVG, bool ANALYTIC>
+template <int MODEL, bool AVG, bool ANALYTIC, class T>
 static cudaError_t launch_one(const PreintParams& p, int grid, int block, cudaStream_t st) {
-    auto kern = k_preintegrate<MODEL, AVG, ANALYTIC>;
+    auto kern = k_preintegrate<MODEL, AVG, ANALYTIC, T>;
     static bool configured = false;     // per instantiation; the attribute is sticky per device context
     static int configured_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured || configured_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes<MODEL>());
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes<MODEL, T>());
         if (e != cudaSuccess) return e;
         configured = true; configured_dev = dev;
     }
-    kern<<<grid, block, tile_bytes<MODEL>(), st>>>(p);
+    kern<<<grid, block, tile_bytes<MODEL, T>(), st>>>(p);
     return cudaGetLastError();
 }
 
 // Windows per block.  Small batches: spread over all SMs in ONE wave (a second wave would double the latency of a
 // latency-bound launch).  Large batches: the tile's compile-time capacity S.
-int preint_pick_wpb(int model, int64_t n_windows, int num_sms, int max_smem_bytes) {
-    (void)max_smem_bytes;
-    const int cap = model == 1 ? Tile<1>::S : Tile<2>::S;
+int preint_pick_wpb(int model, int dtype, int64_t n_windows, int num_sms) {
+    const int cap = dtype == 32 ? (model == 1 ? Tile<1, float>::S : Tile<2, float>::S) : (model == 1 ? Tile<1, double>::S : Tile<2, double>::S);
     const int64_t need = (n_windows + num_sms - 1) / num_sms;
     if (need <= cap) return (int)(need < 1 ? 1 : need);
     return cap;
 }
 
-cudaError_t preint_launch(int model, int flags, const PreintParams& p0, int num_sms, int max_smem_bytes, cudaStream_t st, int* launches) {
+template <class T>
+static cudaError_t launch_typed(int model, int flags, const PreintParams& p, int grid, int block, cudaStream_t st) {
+    const bool avg = flags & CPI_FLAG_IMU_AVG, ana = flags & CPI_FLAG_ANALYTIC_JACOBIANS;
+    if (model == 1) return avg ? launch_one<1, true, false, T>(p, grid, block, st) : launch_one<1, false, false, T>(p, grid, block, st);
+    if (!ana) return avg ? launch_one<2, true, false, T>(p, grid, block, st) : launch_one<2, false, false, T>(p, grid, block, st);
+    return avg ? launch_one<2, true, true, T>(p, grid, block, st) : launch_one<2, false, true, T>(p, grid, block, st);
+}
+
+cudaError_t preint_launch(int model, int dtype, int flags, const PreintParams& p0, int num_sms, int max_smem_bytes, cudaStream_t st, int* launches) {
     PreintParams p = p0;
     if (p.n_windows == 0) return cudaSuccess;
-    if ((size_t)max_smem_bytes < (model == 1 ? tile_bytes<1>() : tile_bytes<2>())) return cudaErrorInvalidConfiguration;
-    p.wpb = preint_pick_wpb(model, p.n_windows, num_sms, max_smem_bytes);
+    if (max_smem_bytes < 232448) return cudaErrorInvalidConfiguration;
+    p.wpb = preint_pick_wpb(model, dtype, p.n_windows, num_sms);
     const int block = (p.wpb + 31) / 32 * 32;
     const int grid = (int)((p.n_windows + p.wpb - 1) / p.wpb);
-    const bool avg = flags & CPI_FLAG_IMU_AVG, ana = flags & CPI_FLAG_ANALYTIC_JACOBIANS;
-    cudaError_t e;
-    if (model == 1) e = avg ? launch_one<1, true, false>(p, grid, block, st) : launch_one<1, false, false>(p, grid, block, st);
-    else if (!ana) e = avg ? launch_one<2, true, false>(p, grid, block, st) : launch_one<2, false, false>(p, grid, block, st);
-    else e = avg ? launch_one<2, true, true>(p, grid, block, st) : launch_one<2, false, true>(p, grid, block, st);
+    cudaError_t e = dtype == 32 ? launch_typed<float>(model, flags, p, grid, block, st) : launch_typed<double>(model, flags, p, grid, block, st);
     if (launches) *launches = 1;
     return e;
 }

@@ -39,14 +39,20 @@ def _tptr(t):
 # batch entry points
 # ------------------------------------------------------------------------------------------------------------------
 
-def preintegrate_host(model, samples, lin, sigmas, flags=0, offsets=None, ns=None):
+def preintegrate_host(model, samples, lin, sigmas, flags=0, offsets=None, ns=None, dtype=None):
     """HOST numpy in, HOST numpy out, through ``cpi_preintegrate_batch_host`` (H2D + kernel + D2H inside the call).
 
     samples: (entries, 7) [wx wy wz ax ay az dt];  lin: (n, 13);  offsets: int64 (n+1) or None with uniform ``ns``.
-    Returns records (n, 290|308)."""
+    dtype: np.float64 (default) or np.float32 = the fp32-storage variant (float samples / lin / records).
+    Returns records (n, 290|308) in that dtype."""
     lib = capi.load()
-    samples = np.ascontiguousarray(samples, dtype=np.float64).reshape(-1, 7)
-    lin = np.ascontiguousarray(lin, dtype=np.float64).reshape(-1, 13)
+    if dtype is None:
+        dtype = np.float32 if getattr(samples, "dtype", None) == np.float32 else np.float64
+    dtype = np.dtype(dtype)
+    if dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+        raise ValueError("dtype must be float64 or float32")
+    samples = np.ascontiguousarray(samples, dtype=dtype).reshape(-1, 7)
+    lin = np.ascontiguousarray(lin, dtype=dtype).reshape(-1, 13)
     sig = np.ascontiguousarray(sigmas, dtype=np.float64)
     n = lin.shape[0]
     avg = 1 if flags & FLAG_IMU_AVG else 0
@@ -62,22 +68,23 @@ def preintegrate_host(model, samples, lin, sigmas, flags=0, offsets=None, ns=Non
             ns = samples.shape[0] // max(n, 1) - avg
         if samples.shape[0] < n * (ns + avg):
             raise ValueError("sample array shorter than n_windows * (ns + imu_avg)")
-    out = np.empty((n, REC_DOUBLES[model]), dtype=np.float64)
-    capi.check(lib.cpi_preintegrate_batch_host(model, 64, n, _ptr(offsets), int(ns), _ptr(samples), _ptr(lin), _ptr(sig),
+    out = np.empty((n, REC_DOUBLES[model]), dtype=dtype)
+    capi.check(lib.cpi_preintegrate_batch_host(model, 8 * dtype.itemsize, n, _ptr(offsets), int(ns), _ptr(samples), _ptr(lin), _ptr(sig),
                                                int(flags), _ptr(out)))
     return out
 
 
 def preintegrate(model, samples, lin, sigmas, flags=0, offsets=None, ns=None, out=None, stream=None):
-    """DEVICE torch tensors in/out (float64, contiguous, all on the current CUDA device); enqueues on ``stream``
-    (a torch.cuda.Stream; default: torch's current stream) and does not synchronise."""
+    """DEVICE torch tensors in/out (float64 -- or float32 for the fp32-storage variant --, contiguous, all on the current
+    CUDA device); enqueues on ``stream`` (a torch.cuda.Stream; default: torch's current stream) and does not synchronise."""
     import torch
 
     lib = capi.load()
     if not (samples.is_cuda and lin.is_cuda):
         raise ValueError("preintegrate() takes CUDA tensors; use preintegrate_host() for host arrays")
-    if samples.dtype != torch.float64 or lin.dtype != torch.float64:
-        raise ValueError("float64 tensors required")
+    if samples.dtype not in (torch.float64, torch.float32) or lin.dtype != samples.dtype:
+        raise ValueError("samples and lin must both be float64 or both float32")
+    tdt = samples.dtype
     samples = samples.contiguous(); lin = lin.contiguous()
     n = lin.numel() // 13
     avg = 1 if flags & FLAG_IMU_AVG else 0
@@ -92,12 +99,12 @@ def preintegrate(model, samples, lin, sigmas, flags=0, offsets=None, ns=None, ou
         if samples.numel() // 7 < n * (ns + avg):
             raise ValueError("sample tensor shorter than n_windows * (ns + imu_avg)")
     if out is None:
-        out = torch.empty((n, REC_DOUBLES[model]), dtype=torch.float64, device=lin.device)
-    elif out.numel() < n * REC_DOUBLES[model] or not out.is_contiguous() or out.dtype != torch.float64:
-        raise ValueError("out must be a contiguous float64 tensor of n_windows * record_doubles")
+        out = torch.empty((n, REC_DOUBLES[model]), dtype=tdt, device=lin.device)
+    elif out.numel() < n * REC_DOUBLES[model] or not out.is_contiguous() or out.dtype != tdt:
+        raise ValueError("out must be a contiguous tensor of n_windows * record_doubles in the input dtype")
     sig = np.ascontiguousarray(sigmas, dtype=np.float64)
     st = stream if stream is not None else torch.cuda.current_stream()
-    capi.check(lib.cpi_preintegrate_batch(model, 64, n, _tptr(offsets), int(ns), _tptr(samples), _tptr(lin), _ptr(sig), int(flags),
+    capi.check(lib.cpi_preintegrate_batch(model, 64 if tdt == torch.float64 else 32, n, _tptr(offsets), int(ns), _tptr(samples), _tptr(lin), _ptr(sig), int(flags),
                                           _tptr(out), ctypes.c_void_p(st.cuda_stream)))
     return out
 

@@ -42,6 +42,7 @@ def test_argument_validation_without_gpu():
     assert rc == -1 and b"model" in lib.cpi_last_error()
     rc = lib.cpi_preintegrate_batch(1, 16, 1, None, 1, None, None, None, 0, None, None)
     assert rc == -1 and b"dtype" in lib.cpi_last_error()
+    assert lib.cpi_preintegrate_batch(1, 32, 0, None, 1, None, None, None, 0, None, None) == 0
     rc = lib.cpi_preintegrate_batch(1, 64, -5, None, 1, None, None, None, 0, None, None)
     assert rc == -1
     assert lib.cpi_preintegrate_batch(1, 64, 0, None, 1, None, None, None, 0, None, None) == 0      # empty batch is a no-op
