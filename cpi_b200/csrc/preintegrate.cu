@@ -18,6 +18,7 @@
 // theta_klin rows/cols of P_big are identically zero and the clone rows are re-initialised from the theta rows every
 // step (B_k, CpiV2.h:436-443).  Its Jacobians are read out of the compounded transition Discrete_J_b; only 7 of its
 // 3x3 blocks are ever non-trivial in the 9 consumed columns, and Phi's RK4 has closed block forms (see phi_blocks()).
+#include <cstdlib>
 #include "cpi_common.cuh"
 #include "cpi_kernels.h"
 
@@ -565,6 +566,224 @@ CPI_DEV void rot_apply(double a, double b, const double* w, const double* R, dou
 }
 
 // =====================================================================================================================
+// Per-sample "front" work: estimated readings, rotation chain (new and mid-point rotation), closed-form means and the
+// analytic bias Jacobians (CpiV1.h:77-259; CpiV2.h:98-305).  Everything the covariance step needs comes out as
+// (wh, ah, g_tau, Rm, R1); R (old rotation) is NOT committed here.  Jacobian state lives in the tile (Jt).
+template <int MODEL, bool AVG, bool ANALYTIC, int S>
+CPI_DEV void front_step(const double* s0, const double* nx, const double* bw, const double* ba, const double* g_k, const double* R,
+                        double* alpha, double* beta, double* Jt, double* wh, double* ah, double* g_tau, double* Rm, double* R1) {
+    const double dt = s0[6];
+    // ---- estimated readings (CpiV1.h:77-86; CpiV2.h:98-106)
+    wh[0] = s0[0] - bw[0]; wh[1] = s0[1] - bw[1]; wh[2] = s0[2] - bw[2];
+    ah[0] = s0[3] - ba[0]; ah[1] = s0[4] - ba[1]; ah[2] = s0[5] - ba[2];
+    g_tau[0] = g_tau[1] = g_tau[2] = 0.0;
+    if (MODEL == 2) {
+        mv33(R, g_k, g_tau);                         // R_k2tau * R_G_to_k * grav  (old R)
+        ah[0] -= g_tau[0]; ah[1] -= g_tau[1]; ah[2] -= g_tau[2];
+    }
+    if (AVG) {
+#pragma unroll
+        for (int e = 0; e < 3; e++) { wh[e] += nx[e] - bw[e]; wh[e] = 0.5 * wh[e]; }
+        if (MODEL == 1) {
+#pragma unroll
+            for (int e = 0; e < 3; e++) { ah[e] += nx[3 + e] - ba[e]; ah[e] = 0.5 * ah[e]; }
+        }
+    }
+    const double mag2 = wh[0] * wh[0] + wh[1] * wh[1] + wh[2] * wh[2];
+    const double mag = sqrt(mag2);
+    const double th = mag * dt;
+    const bool small_w = mag < 0.008726646;          // CpiV1.h:101
+    double sn, cs_, sh, ch;
+    sincos(th, &sn, &cs_);
+    sincos(mag * 0.5 * dt, &sh, &ch);
+    // one reciprocal instead of ~16 divisions (each an ~40-instruction subroutine); never used when small_w
+    const double im = small_w ? 0.0 : 1.0 / mag;
+    const double im2 = im * im;
+
+    // ---- relative rotation, new and mid rotation (CpiV1.h:119-124, 267-269)
+    const double a1 = small_w ? dt : sn * im, b1 = small_w ? (dt * dt) * 0.5 : (1.0 - cs_) * im2;
+    rot_apply(a1, b1, wh, R, R1);
+    {
+        const double hd = 0.5 * dt;
+        const double a2 = small_w ? hd : sh * im, b2 = small_w ? (hd * hd) * 0.5 : (1.0 - ch) * im2;
+        rot_apply(a2, b2, wh, R, Rm);
+    }
+    if (MODEL == 2 && AVG) {                         // CpiV2.h:146-149: average the LOCAL acceleration with the NEW rotation
+        double g1[3];
+        mv33(R1, g_k, g1);
+#pragma unroll
+        for (int e = 0; e < 3; e++) { ah[e] += nx[3 + e] - ba[e] - g1[e]; ah[e] = 0.5 * ah[e]; }
+    }
+
+    // ---- closed-form coefficients (CpiV1.h:132-142, 196-238 == CpiV2.h:158-168, 231-274)
+    double f1, f2, f3, f4, d1, d2, d3, d4;
+    {
+        const double dt2 = dt * dt, dt3 = dt2 * dt;
+        if (small_w) {
+            f1 = -(dt3 / 3.0); f2 = (dt2 * dt2) / 8.0; f3 = -(dt2 / 2.0); f4 = dt3 / 6.0;
+            d1 = -(dt3 * dt2 / 15.0); d2 = (dt3 * dt3) / 72.0; d3 = -(dt2 * dt2 / 12.0); d4 = (dt3 * dt2) / 60.0;
+        } else {
+            const double im3 = im2 * im, im4 = im2 * im2, th2 = th * th;
+            f1 = (th * cs_ - sn) * im3;
+            f2 = (th2 - 2.0 * cs_ - 2.0 * th * sn + 2.0) * (0.5 * im4);
+            f3 = -(1.0 - cs_) * im2;
+            f4 = (th - sn) * im3;
+            if (MODEL == 1 || ANALYTIC) {
+                d1 = (th2 * sn - 3.0 * sn + 3.0 * th * cs_) * (im4 * im);
+                d2 = (th2 - 4.0 * cs_ - 4.0 * th * sn + th2 * cs_ + 4.0) * (im4 * im2);
+                d3 = (2.0 * (cs_ - 1.0) + th * sn) * im4;
+                d4 = (2.0 * th + th * cs_ - 3.0 * sn) * (im4 * im);
+            }
+        }
+    }
+
+    // W and W^2 entries
+    const double W2[9] = {-(wh[1] * wh[1] + wh[2] * wh[2]), wh[0] * wh[1], wh[0] * wh[2],
+                          wh[0] * wh[1], -(wh[0] * wh[0] + wh[2] * wh[2]), wh[1] * wh[2],
+                          wh[0] * wh[2], wh[1] * wh[2], -(wh[0] * wh[0] + wh[1] * wh[1])};
+    const double Wm[9] = {0.0, -wh[2], wh[1], wh[2], 0.0, -wh[0], -wh[1], wh[0], 0.0};
+    double aarg[9], barg[9], Hal[9], Hbe[9];
+    {
+        const double hdt2 = (dt * dt) * 0.5;
+#pragma unroll
+        for (int e = 0; e < 9; e++) {
+            aarg[e] = ((e % 4 == 0) ? hdt2 : 0.0) + f1 * Wm[e] + f2 * W2[e];     // CpiV1.h:145
+            barg[e] = ((e % 4 == 0) ? dt : 0.0) + f3 * Wm[e] + f4 * W2[e];       // CpiV1.h:146
+        }
+    }
+    mulT33(R1, aarg, Hal);                            // R_tau12k * alpha_arg
+    mulT33(R1, barg, Hbe);
+    {
+        double t3[3];
+        mv33(Hal, ah, t3);
+#pragma unroll
+        for (int e = 0; e < 3; e++) alpha[e] += beta[e] * dt + t3[e];   // CpiV1.h:153 (old beta)
+        mv33(Hbe, ah, t3);
+#pragma unroll
+        for (int e = 0; e < 3; e++) beta[e] += t3[e];                   // CpiV1.h:154
+    }
+
+    if (MODEL == 1 || ANALYTIC) {
+        // ---- analytic bias Jacobians (CpiV1.h:162-259; CpiV2.h:188-305); state lives in the tile, not in registers
+        double Jq[9], Jsave[9];
+        ld9<S>(Jt, J_Q, Jq);
+#pragma unroll
+        for (int e = 0; e < 9; e++) Jsave[e] = Jq[e];
+        {
+            const double ith = small_w ? 0.0 : 1.0 / th;
+            const double c1 = small_w ? 0.5 : (1.0 - cs_) * (ith * ith), c2 = small_w ? (1.0 / 6.0) : (th - sn) * (ith * ith * ith);
+            double t9[9];
+            rot_apply(a1, b1, wh, Jsave, t9);         // R_tau2tau1 * J_q
+            const double ca = c1 * dt, cb = c2 * dt * dt;   // w_tx = dt*W, w_tx^2 = dt^2 W2
+#pragma unroll
+            for (int e = 0; e < 9; e++) {
+                Jq[e] = t9[e] + (((e % 4 == 0) ? 1.0 : 0.0) - ca * Wm[e] + cb * W2[e]) * dt;   // CpiV1.h:167
+                SM(Jt, J_Q + e) = Jq[e];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 9; e++) {                  // CpiV1.h:170-172 (old H_b)
+            const double hb = SM(Jt, H_B + e);
+            SM(Jt, H_A + e) = (SM(Jt, H_A + e) - Hal[e]) + dt * hb;
+            SM(Jt, H_B + e) = hb - Hbe[e];
+        }
+        if (MODEL == 2) {                              // CpiV2.h:203-205
+            const double sk[9] = {0.0, -g_k[2], g_k[1], g_k[2], 0.0, -g_k[0], -g_k[1], g_k[0], 0.0};
+            double t1[9], t2[9], t4[9];
+            mul33(R, sk, t1);
+            mul33(Hal, t1, t2);
+            mul33(Hbe, t1, t4);
+#pragma unroll
+            for (int e = 0; e < 9; e++) {
+                const double ob = SM(Jt, O_B + e);
+                SM(Jt, O_A + e) = (SM(Jt, O_A + e) + dt * ob) + -t2[e];
+                SM(Jt, O_B + e) = ob + -t4[e];
+            }
+        }
+        // vectors shared by the three columns
+        double ua[3], ub[3], Wa[3], W2a[3];
+        mv33(aarg, ah, ua); mv33(barg, ah, ub);
+        cross(wh, ah, Wa);                             // W a = w x a
+        cross(wh, Wa, W2a);                            // W^2 a
+#pragma unroll
+        for (int col = 0; col < 3; col++) {
+            const double e3[3] = {col == 0 ? 1.0 : 0.0, col == 1 ? 1.0 : 0.0, col == 2 ? 1.0 : 0.0};
+            const double jc[3] = {Jq[col], Jq[3 + col], Jq[6 + col]};   // NEW J_q e_i
+            double exa[3], exWa[3], Wexa[3], c1v[3], c2v[3], va_[3], vb_[3], oa3[3], ob3[3];
+            cross(e3, ah, exa);                        // e_ix a
+            cross(e3, Wa, exWa);                       // e_ix W a
+            cross(wh, exa, Wexa);                      // W e_ix a
+            cross(jc, ua, c1v);                        // [J_q e_i x] (alpha_arg a)
+            cross(jc, ub, c2v);
+            const double wi = wh[col];
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                va_[e] = -c1v[e] + (wi * d1) * Wa[e] - f1 * exa[e] + (wi * d2) * W2a[e] - f2 * (exWa[e] + Wexa[e]);
+                vb_[e] = -c2v[e] + (wi * d3) * Wa[e] - f3 * exa[e] + (wi * d4) * W2a[e] - f4 * (exWa[e] + Wexa[e]);
+            }
+            mvT33(R1, va_, oa3);
+            mvT33(R1, vb_, ob3);
+            if (MODEL == 2) {                          // - H_al [J_save e_i x] g_tau (CpiV2.h:285-293); J_b column 0 carries
+                const double js[3] = {Jsave[col], Jsave[3 + col], Jsave[6 + col]};   // the reference's "- -" = plus (:296-297)
+                double cg[3], u[3];
+                cross(js, g_tau, cg);
+                mv33(Hal, cg, u);
+                oa3[0] -= u[0]; oa3[1] -= u[1]; oa3[2] -= u[2];
+                mv33(Hbe, cg, u);
+                if (col == 0) { ob3[0] += u[0]; ob3[1] += u[1]; ob3[2] += u[2]; }
+                else { ob3[0] -= u[0]; ob3[1] -= u[1]; ob3[2] -= u[2]; }
+            }
+#pragma unroll
+            for (int r = 0; r < 3; r++) {              // J_a += J_b*dt (old J_b, CpiV1.h:241) then the column terms
+                const double jb = SM(Jt, J_B + 3 * r + col);
+                SM(Jt, J_A + 3 * r + col) = (SM(Jt, J_A + 3 * r + col) + jb * dt) + oa3[r];
+                SM(Jt, J_B + 3 * r + col) = jb + ob3[r];
+            }
+        }
+    }
+
+}
+
+// ---- TMA-staged sample fetch (non-imu_avg path), shared by the fused and the warp-specialised kernels ----------------
+template <class T> struct Fetch {
+    static constexpr int EPL = 16 / (int)sizeof(T);      // elements per 16 bytes
+    static constexpr int CH = 8 / (int)sizeof(T) * 2;    // samples per chunk: 2 (fp64) or 4 (fp32) = 112 B
+    const T* sp; const T* buf; uint32_t buf0, bar0; int shift; int64_t n_tma;
+    CPI_DEV void init(const T* sp_, int64_t o0, int64_t nsteps, const T* buf_, uint32_t bar0_) {
+        sp = sp_; buf = buf_; buf0 = smem_u32(buf_); bar0 = bar0_;
+        shift = (int)((7 * o0) % EPL);
+        n_tma = nsteps > 0 ? (nsteps - 1) / CH : 0;
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+            if (c < n_tma) {
+                mbar_arrive_expect_tx(bar0 + 8 * c, 128);
+                bulk_g2s(buf0 + 128 * c, sp + 7 * CH * c - shift, 128, bar0 + 8 * c);
+            }
+    }
+    CPI_DEV void get(int64_t it, double* s0) {
+        if (it < CH * n_tma) {
+            const int64_t c = it / CH;
+            const int b = (int)(c & 1), j = (int)(it % CH);
+            if (j == 0) mbar_wait(bar0 + 8 * b, (uint32_t)((c >> 1) & 1));
+            const T* src = buf + b * (128 / (int)sizeof(T)) + shift + 7 * j;
+#pragma unroll
+            for (int e = 0; e < 7; e++) s0[e] = (double)src[e];
+            if (j == CH - 1 && c + 2 < n_tma) {
+                fence_proxy_async();
+                mbar_arrive_expect_tx(bar0 + 8 * b, 128);
+                bulk_g2s(buf0 + 128 * b, sp + 7 * CH * (c + 2) - shift, 128, bar0 + 8 * b);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 7; e++) s0[e] = (double)__ldg(sp + it * CPI_SAMPLE_DOUBLES + e);
+        }
+    }
+};
+
+// =====================================================================================================================
 // Sample stream: per-window contiguous entries of 7 doubles.  Default mode stages it with 1-D TMA bulk copies
 // (cp.async.bulk -> SASS UBLKCP): every lane owns two 128-byte line buffers and two mbarriers and keeps two chunks of
 // two samples (112 B, fetched as ONE aligned 128-byte transaction that also covers the 8-byte misalignment of odd
@@ -657,175 +876,8 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
         DT += dt;                                        // CpiV1.h:69
         if (dt == 0.0) continue;                         // CpiV1.h:72-74
 
-        // ---- estimated readings (CpiV1.h:77-86; CpiV2.h:98-106)
-        double wh[3] = {s0[0] - bw[0], s0[1] - bw[1], s0[2] - bw[2]};
-        double ah[3] = {s0[3] - ba[0], s0[4] - ba[1], s0[5] - ba[2]};
-        double g_tau[3] = {0, 0, 0};
-        if (MODEL == 2) {
-            mv33(R, g_k, g_tau);                         // R_k2tau * R_G_to_k * grav  (old R)
-            ah[0] -= g_tau[0]; ah[1] -= g_tau[1]; ah[2] -= g_tau[2];
-        }
-        if (AVG) {
-#pragma unroll
-            for (int e = 0; e < 3; e++) { wh[e] += nx[e] - bw[e]; wh[e] = 0.5 * wh[e]; }
-            if (MODEL == 1) {
-#pragma unroll
-                for (int e = 0; e < 3; e++) { ah[e] += nx[3 + e] - ba[e]; ah[e] = 0.5 * ah[e]; }
-            }
-        }
-        const double mag2 = wh[0] * wh[0] + wh[1] * wh[1] + wh[2] * wh[2];
-        const double mag = sqrt(mag2);
-        const double th = mag * dt;
-        const bool small_w = mag < 0.008726646;          // CpiV1.h:101
-        double sn, cs_, sh, ch;
-        sincos(th, &sn, &cs_);
-        sincos(mag * 0.5 * dt, &sh, &ch);
-        // one reciprocal instead of ~16 divisions (each an ~40-instruction subroutine); never used when small_w
-        const double im = small_w ? 0.0 : 1.0 / mag;
-        const double im2 = im * im;
-
-        // ---- relative rotation, new and mid rotation (CpiV1.h:119-124, 267-269)
-        const double a1 = small_w ? dt : sn * im, b1 = small_w ? (dt * dt) * 0.5 : (1.0 - cs_) * im2;
-        double R1[9], Rm[9];
-        rot_apply(a1, b1, wh, R, R1);
-        {
-            const double hd = 0.5 * dt;
-            const double a2 = small_w ? hd : sh * im, b2 = small_w ? (hd * hd) * 0.5 : (1.0 - ch) * im2;
-            rot_apply(a2, b2, wh, R, Rm);
-        }
-        if (MODEL == 2 && AVG) {                         // CpiV2.h:146-149: average the LOCAL acceleration with the NEW rotation
-            double g1[3];
-            mv33(R1, g_k, g1);
-#pragma unroll
-            for (int e = 0; e < 3; e++) { ah[e] += nx[3 + e] - ba[e] - g1[e]; ah[e] = 0.5 * ah[e]; }
-        }
-
-        // ---- closed-form coefficients (CpiV1.h:132-142, 196-238 == CpiV2.h:158-168, 231-274)
-        double f1, f2, f3, f4, d1, d2, d3, d4;
-        {
-            const double dt2 = dt * dt, dt3 = dt2 * dt;
-            if (small_w) {
-                f1 = -(dt3 / 3.0); f2 = (dt2 * dt2) / 8.0; f3 = -(dt2 / 2.0); f4 = dt3 / 6.0;
-                d1 = -(dt3 * dt2 / 15.0); d2 = (dt3 * dt3) / 72.0; d3 = -(dt2 * dt2 / 12.0); d4 = (dt3 * dt2) / 60.0;
-            } else {
-                const double im3 = im2 * im, im4 = im2 * im2, th2 = th * th;
-                f1 = (th * cs_ - sn) * im3;
-                f2 = (th2 - 2.0 * cs_ - 2.0 * th * sn + 2.0) * (0.5 * im4);
-                f3 = -(1.0 - cs_) * im2;
-                f4 = (th - sn) * im3;
-                if (MODEL == 1 || ANALYTIC) {
-                    d1 = (th2 * sn - 3.0 * sn + 3.0 * th * cs_) * (im4 * im);
-                    d2 = (th2 - 4.0 * cs_ - 4.0 * th * sn + th2 * cs_ + 4.0) * (im4 * im2);
-                    d3 = (2.0 * (cs_ - 1.0) + th * sn) * im4;
-                    d4 = (2.0 * th + th * cs_ - 3.0 * sn) * (im4 * im);
-                }
-            }
-        }
-
-        // W and W^2 entries
-        const double W2[9] = {-(wh[1] * wh[1] + wh[2] * wh[2]), wh[0] * wh[1], wh[0] * wh[2],
-                              wh[0] * wh[1], -(wh[0] * wh[0] + wh[2] * wh[2]), wh[1] * wh[2],
-                              wh[0] * wh[2], wh[1] * wh[2], -(wh[0] * wh[0] + wh[1] * wh[1])};
-        const double Wm[9] = {0.0, -wh[2], wh[1], wh[2], 0.0, -wh[0], -wh[1], wh[0], 0.0};
-        double aarg[9], barg[9], Hal[9], Hbe[9];
-        {
-            const double hdt2 = (dt * dt) * 0.5;
-#pragma unroll
-            for (int e = 0; e < 9; e++) {
-                aarg[e] = ((e % 4 == 0) ? hdt2 : 0.0) + f1 * Wm[e] + f2 * W2[e];     // CpiV1.h:145
-                barg[e] = ((e % 4 == 0) ? dt : 0.0) + f3 * Wm[e] + f4 * W2[e];       // CpiV1.h:146
-            }
-        }
-        mulT33(R1, aarg, Hal);                            // R_tau12k * alpha_arg
-        mulT33(R1, barg, Hbe);
-        {
-            double t3[3];
-            mv33(Hal, ah, t3);
-#pragma unroll
-            for (int e = 0; e < 3; e++) alpha[e] += beta[e] * dt + t3[e];   // CpiV1.h:153 (old beta)
-            mv33(Hbe, ah, t3);
-#pragma unroll
-            for (int e = 0; e < 3; e++) beta[e] += t3[e];                   // CpiV1.h:154
-        }
-
-        if (MODEL == 1 || ANALYTIC) {
-            // ---- analytic bias Jacobians (CpiV1.h:162-259; CpiV2.h:188-305); state lives in the tile, not in registers
-            double Jq[9], Jsave[9];
-            ld9<S>(Jt, J_Q, Jq);
-#pragma unroll
-            for (int e = 0; e < 9; e++) Jsave[e] = Jq[e];
-            {
-                const double ith = small_w ? 0.0 : 1.0 / th;
-                const double c1 = small_w ? 0.5 : (1.0 - cs_) * (ith * ith), c2 = small_w ? (1.0 / 6.0) : (th - sn) * (ith * ith * ith);
-                double t9[9];
-                rot_apply(a1, b1, wh, Jsave, t9);         // R_tau2tau1 * J_q
-                const double ca = c1 * dt, cb = c2 * dt * dt;   // w_tx = dt*W, w_tx^2 = dt^2 W2
-#pragma unroll
-                for (int e = 0; e < 9; e++) {
-                    Jq[e] = t9[e] + (((e % 4 == 0) ? 1.0 : 0.0) - ca * Wm[e] + cb * W2[e]) * dt;   // CpiV1.h:167
-                    SM(Jt, J_Q + e) = Jq[e];
-                }
-            }
-#pragma unroll
-            for (int e = 0; e < 9; e++) {                  // CpiV1.h:170-172 (old H_b)
-                const double hb = SM(Jt, H_B + e);
-                SM(Jt, H_A + e) = (SM(Jt, H_A + e) - Hal[e]) + dt * hb;
-                SM(Jt, H_B + e) = hb - Hbe[e];
-            }
-            if (MODEL == 2) {                              // CpiV2.h:203-205
-                const double sk[9] = {0.0, -g_k[2], g_k[1], g_k[2], 0.0, -g_k[0], -g_k[1], g_k[0], 0.0};
-                double t1[9], t2[9], t4[9];
-                mul33(R, sk, t1);
-                mul33(Hal, t1, t2);
-                mul33(Hbe, t1, t4);
-#pragma unroll
-                for (int e = 0; e < 9; e++) {
-                    const double ob = SM(Jt, O_B + e);
-                    SM(Jt, O_A + e) = (SM(Jt, O_A + e) + dt * ob) + -t2[e];
-                    SM(Jt, O_B + e) = ob + -t4[e];
-                }
-            }
-            // vectors shared by the three columns
-            double ua[3], ub[3], Wa[3], W2a[3];
-            mv33(aarg, ah, ua); mv33(barg, ah, ub);
-            cross(wh, ah, Wa);                             // W a = w x a
-            cross(wh, Wa, W2a);                            // W^2 a
-#pragma unroll
-            for (int col = 0; col < 3; col++) {
-                const double e3[3] = {col == 0 ? 1.0 : 0.0, col == 1 ? 1.0 : 0.0, col == 2 ? 1.0 : 0.0};
-                const double jc[3] = {Jq[col], Jq[3 + col], Jq[6 + col]};   // NEW J_q e_i
-                double exa[3], exWa[3], Wexa[3], c1v[3], c2v[3], va_[3], vb_[3], oa3[3], ob3[3];
-                cross(e3, ah, exa);                        // e_ix a
-                cross(e3, Wa, exWa);                       // e_ix W a
-                cross(wh, exa, Wexa);                      // W e_ix a
-                cross(jc, ua, c1v);                        // [J_q e_i x] (alpha_arg a)
-                cross(jc, ub, c2v);
-                const double wi = wh[col];
-#pragma unroll
-                for (int e = 0; e < 3; e++) {
-                    va_[e] = -c1v[e] + (wi * d1) * Wa[e] - f1 * exa[e] + (wi * d2) * W2a[e] - f2 * (exWa[e] + Wexa[e]);
-                    vb_[e] = -c2v[e] + (wi * d3) * Wa[e] - f3 * exa[e] + (wi * d4) * W2a[e] - f4 * (exWa[e] + Wexa[e]);
-                }
-                mvT33(R1, va_, oa3);
-                mvT33(R1, vb_, ob3);
-                if (MODEL == 2) {                          // - H_al [J_save e_i x] g_tau (CpiV2.h:285-293); J_b column 0 carries
-                    const double js[3] = {Jsave[col], Jsave[3 + col], Jsave[6 + col]};   // the reference's "- -" = plus (:296-297)
-                    double cg[3], u[3];
-                    cross(js, g_tau, cg);
-                    mv33(Hal, cg, u);
-                    oa3[0] -= u[0]; oa3[1] -= u[1]; oa3[2] -= u[2];
-                    mv33(Hbe, cg, u);
-                    if (col == 0) { ob3[0] += u[0]; ob3[1] += u[1]; ob3[2] += u[2]; }
-                    else { ob3[0] -= u[0]; ob3[1] -= u[1]; ob3[2] -= u[2]; }
-                }
-#pragma unroll
-                for (int r = 0; r < 3; r++) {              // J_a += J_b*dt (old J_b, CpiV1.h:241) then the column terms
-                    const double jb = SM(Jt, J_B + 3 * r + col);
-                    SM(Jt, J_A + 3 * r + col) = (SM(Jt, J_A + 3 * r + col) + jb * dt) + oa3[r];
-                    SM(Jt, J_B + 3 * r + col) = jb + ob3[r];
-                }
-            }
-        }
+        double wh[3], ah[3], g_tau[3], Rm[9], R1[9];
+        front_step<MODEL, AVG, ANALYTIC, S>(s0, nx, bw, ba, g_k, R, alpha, beta, Jt, wh, ah, g_tau, Rm, R1);
 
         // ---- covariance: the reference's RK4, block-serial on the block-triangular Lyapunov operator (rk4_cascade)
         const double hdt = dt * 0.5, dt6 = dt / 6.0;
@@ -1022,6 +1074,197 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
         }
 }
 
+// =====================================================================================================================
+// Warp-specialised variant (model 1, no imu_avg): the per-sample critical path is split over TWO warps that work on the
+// same 32 windows, software-pipelined one sample apart:
+//     FRONT warp: sample fetch (TMA), rotation chain, closed-form means, analytic bias Jacobians      (~2.1 k instr/sample)
+//     BACK  warp: the covariance RK4 cascade                                                          (~3.4 k instr/sample)
+// FRONT hands (R_mid, R_new, w_hat, a_hat, dt) to BACK through a double-buffered shared-memory mailbox guarded by
+// full/empty mbarriers per warp pair.  Small batches are single-warp-latency bound (148 windows take 85 % of the time of
+// 10 000), so shortening the per-warp chain by ~1.6x is the lever there; large batches gain from twice as many resident
+// warps for the same tile footprint.
+enum : int { H_RM = 0, H_R1 = 9, H_W = 18, H_A_ = 21, H_DT = 24, NHAND = 26 };
+template <class T> struct TileWS {
+    static constexpr int NSLOT = 99, NJ = 45, S = sizeof(T) == 8 ? 70 : 96;
+    static constexpr size_t off_T = (size_t)NJ * S * 8;
+    static constexpr size_t off_buf = off_T + (size_t)(2 * NP + NSLOT) * S * sizeof(T);
+    static constexpr size_t off_bar = off_buf + (size_t)S * 256;
+    static constexpr size_t off_hand = off_bar + (size_t)S * 16;
+    static constexpr size_t off_pair = off_hand + (size_t)2 * NHAND * S * 8;
+    static constexpr size_t bytes = off_pair + (size_t)((S + 31) / 32) * 32;
+};
+static_assert(TileWS<double>::bytes <= 232448 && TileWS<float>::bytes <= 232448, "ws tile exceeds 227 KB");
+static_assert(TileWS<double>::off_buf % 16 == 0 && TileWS<float>::off_buf % 16 == 0 && TileWS<double>::off_pair % 8 == 0, "alignment");
+
+CPI_DEV void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+template <class T>
+__global__ void __launch_bounds__(256, 1) k_preintegrate_ws(const PreintParams p) {
+    using TL = TileWS<T>;
+    constexpr int S = TL::S;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nw = (p.wpb + 31) >> 5;                     // warps per role
+    const int role = threadIdx.x >= nw * 32;             // 0 = FRONT, 1 = BACK
+    const int tid = threadIdx.x - role * nw * 32;        // window lane within the CTA
+    const int64_t win = (int64_t)blockIdx.x * p.wpb + tid;
+    const bool active = tid < p.wpb && win < p.n_windows;
+
+    double* Jt = reinterpret_cast<double*>(smem_raw) + tid;
+    T* P = reinterpret_cast<T*>(smem_raw + TL::off_T) + tid;
+    T* Pn = P + (size_t)NP * S;
+    T* sl = P + (size_t)2 * NP * S;
+    double* hand = reinterpret_cast<double*>(smem_raw + TL::off_hand) + tid;
+    const uint32_t pair = smem_u32(smem_raw + TL::off_pair + (size_t)(tid >> 5) * 32);   // full[0], full[1], empty[0], empty[1]
+
+    int64_t o0 = 0, nsteps = 0;
+    if (active) {
+        if (p.offsets) { o0 = p.offsets[win]; nsteps = p.offsets[win + 1] - o0; }
+        else { o0 = win * p.ns_uniform; nsteps = p.ns_uniform; }
+        if (nsteps < 0) nsteps = 0;
+    }
+    const int wmax = __reduce_max_sync(0xffffffffu, (int)nsteps);
+    if (role == 0 && (tid & 31) == 0) {
+        mbar_init(pair, 32); mbar_init(pair + 8, 32); mbar_init(pair + 16, 32); mbar_init(pair + 24, 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    constexpr int RD = CPI_REC_V1_DOUBLES;
+    T* rec = reinterpret_cast<T*>(p.out) + win * (int64_t)RD;
+
+    if (role == 0) {
+        // ------------------------------------------------------------------ FRONT
+        double bw[3] = {0, 0, 0}, ba[3] = {0, 0, 0};
+        const double g_k[3] = {0, 0, 0};
+        Fetch<T> f;
+        if (active) {
+            const T* lin = reinterpret_cast<const T*>(p.lin) + win * CPI_LIN_DOUBLES;
+            bw[0] = (double)lin[0]; bw[1] = (double)lin[1]; bw[2] = (double)lin[2];
+            ba[0] = (double)lin[3]; ba[1] = (double)lin[4]; ba[2] = (double)lin[5];
+            f.init(reinterpret_cast<const T*>(p.samples) + o0 * CPI_SAMPLE_DOUBLES, o0, nsteps,
+                   reinterpret_cast<const T*>(smem_raw + TL::off_buf + (size_t)tid * 256), smem_u32(smem_raw + TL::off_bar + (size_t)tid * 16));
+        }
+        double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        double alpha[3] = {0, 0, 0}, beta[3] = {0, 0, 0}, DT = 0.0;
+#pragma unroll 1
+        for (int e = 0; e < TL::NJ; e++) SM(Jt, e) = 0.0;
+#pragma unroll 1
+        for (int it = 0; it < wmax; it++) {
+            const int b = it & 1;
+            mbar_wait(pair + 16 + 8 * b, (uint32_t)(((it >> 1) & 1) ^ 1));        // mailbox b is free
+            double dt = 0.0;
+            if (it < nsteps) {
+                double s0[7], nx[6], wh[3], ah[3], g_tau[3], Rm[9], R1[9];
+                f.get(it, s0);
+                dt = s0[6];
+                DT += dt;                                                          // CpiV1.h:69
+                if (dt != 0.0) {                                                   // CpiV1.h:72-74
+                    front_step<1, false, false, S>(s0, nx, bw, ba, g_k, R, alpha, beta, Jt, wh, ah, g_tau, Rm, R1);
+#pragma unroll
+                    for (int e = 0; e < 9; e++) { SM(hand, b * NHAND + H_RM + e) = Rm[e]; SM(hand, b * NHAND + H_R1 + e) = R1[e]; R[e] = R1[e]; }
+#pragma unroll
+                    for (int e = 0; e < 3; e++) { SM(hand, b * NHAND + H_W + e) = wh[e]; SM(hand, b * NHAND + H_A_ + e) = ah[e]; }
+                }
+            }
+            SM(hand, b * NHAND + H_DT) = dt;
+            mbar_arrive(pair + 8 * b);                                             // mailbox b is full
+        }
+        if (active) {
+            double q[4];
+            rot_2_quat(R, q);                              // CpiV1.h:358
+            rec[CPI_REC_Q] = (T)q[0]; rec[CPI_REC_Q + 1] = (T)q[1]; rec[CPI_REC_Q + 2] = (T)q[2]; rec[CPI_REC_Q + 3] = (T)q[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    rec[CPI_REC_R + i + 3 * j] = (T)R[3 * i + j];
+                    rec[CPI_REC_JQ + i + 3 * j] = (T)SM(Jt, J_Q + 3 * i + j);
+                    rec[CPI_REC_JA + i + 3 * j] = (T)SM(Jt, J_A + 3 * i + j);
+                    rec[CPI_REC_JB + i + 3 * j] = (T)SM(Jt, J_B + 3 * i + j);
+                    rec[CPI_REC_HA + i + 3 * j] = (T)SM(Jt, H_A + 3 * i + j);
+                    rec[CPI_REC_HB + i + 3 * j] = (T)SM(Jt, H_B + 3 * i + j);
+                }
+#pragma unroll
+            for (int e = 0; e < 3; e++) { rec[CPI_REC_ALPHA + e] = (T)alpha[e]; rec[CPI_REC_BETA + e] = (T)beta[e]; }
+            rec[CPI_REC_DT] = (T)DT;
+        }
+    } else {
+        // ------------------------------------------------------------------ BACK
+        double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        double pgg = 0.0, paa = 0.0;
+        const double g0[3] = {0, 0, 0};
+#pragma unroll 1
+        for (int e = 0; e < NP; e++) SM(P, e) = T(0);
+#pragma unroll 1
+        for (int it = 0; it < wmax; it++) {
+            const int b = it & 1;
+            mbar_wait(pair + 8 * b, (uint32_t)((it >> 1) & 1));                    // mailbox b is full
+            const double dt = SM(hand, b * NHAND + H_DT);
+            if (dt != 0.0) {
+                double wh[3], ah[3], Rm[9], R1[9];
+#pragma unroll
+                for (int e = 0; e < 9; e++) { Rm[e] = SM(hand, b * NHAND + H_RM + e); R1[e] = SM(hand, b * NHAND + H_R1 + e); }
+#pragma unroll
+                for (int e = 0; e < 3; e++) { wh[e] = SM(hand, b * NHAND + H_W + e); ah[e] = SM(hand, b * NHAND + H_A_ + e); }
+                mbar_arrive(pair + 16 + 8 * b);                                    // mailbox b is free again
+                rk4_cascade<1, S, T>(P, Pn, sl, wh, ah, g0, R, Rm, R1, pgg, paa, dt, p.q_w, p.q_wb, p.q_a, p.q_ab);
+                { T* t = P; P = Pn; Pn = t; }
+                const double dt6 = dt / 6.0;
+                pgg += dt6 * (p.q_wb + 2.0 * p.q_wb + 2.0 * p.q_wb + p.q_wb);
+                paa += dt6 * (p.q_ab + 2.0 * p.q_ab + 2.0 * p.q_ab + p.q_ab);
+#pragma unroll
+                for (int e = 0; e < 9; e++) R[e] = R1[e];
+            } else {
+                mbar_arrive(pair + 16 + 8 * b);
+            }
+        }
+        if (active) {
+            T* Pm = rec + CPI_REC_P;
+            auto put = [&](int r, int c, T v) { Pm[r + 15 * c] = v; };
+#pragma unroll 1
+            for (int i = 0; i < 3; i++)
+#pragma unroll 1
+                for (int j = 0; j < 3; j++) {
+                    const int sidx = sym3(i, j);
+                    put(i, j, SM(P, TT + sidx));            put(6 + i, 6 + j, SM(P, VV + sidx));      put(12 + i, 12 + j, SM(P, PP + sidx));
+                    put(3 + i, 3 + j, i == j ? (T)pgg : T(0));  put(9 + i, 9 + j, i == j ? (T)paa : T(0));
+                    put(i, 9 + j, T(0)); put(9 + j, i, T(0)); put(3 + i, 9 + j, T(0)); put(9 + j, 3 + i, T(0));
+                    T v;
+                    v = SM(P, TG + 3 * i + j); put(i, 3 + j, v);      put(3 + j, i, v);
+                    v = SM(P, VT + 3 * i + j); put(6 + i, j, v);      put(j, 6 + i, v);
+                    v = SM(P, VG + 3 * i + j); put(6 + i, 3 + j, v);  put(3 + j, 6 + i, v);
+                    v = SM(P, VA + 3 * i + j); put(6 + i, 9 + j, v);  put(9 + j, 6 + i, v);
+                    v = SM(P, PT + 3 * i + j); put(12 + i, j, v);     put(j, 12 + i, v);
+                    v = SM(P, PG + 3 * i + j); put(12 + i, 3 + j, v); put(3 + j, 12 + i, v);
+                    v = SM(P, PV + 3 * i + j); put(12 + i, 6 + j, v); put(6 + j, 12 + i, v);
+                    v = SM(P, PA + 3 * i + j); put(12 + i, 9 + j, v); put(9 + j, 12 + i, v);
+                }
+        }
+    }
+}
+
+template <class T>
+static cudaError_t launch_ws(const PreintParams& p0, int num_sms, cudaStream_t st) {
+    PreintParams p = p0;
+    auto kern = k_preintegrate_ws<T>;
+    static bool configured = false;
+    static int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured || configured_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileWS<T>::bytes);
+        if (e != cudaSuccess) return e;
+        configured = true; configured_dev = dev;
+    }
+    const int cap = TileWS<T>::S;
+    const int64_t need = (p.n_windows + num_sms - 1) / num_sms;
+    p.wpb = (int)(need <= cap ? (need < 1 ? 1 : need) : cap);
+    const int block = 2 * ((p.wpb + 31) / 32 * 32);
+    const int grid = (int)((p.n_windows + p.wpb - 1) / p.wpb);
+    kern<<<grid, block, TileWS<T>::bytes, st>>>(p);
+    return cudaGetLastError();
+}
+
 // ---- host-side launcher (called from capi.cu) --------------------------------------------------------------------------
 template <int MODEL, bool AVG, bool ANALYTIC, class T>
 static cudaError_t launch_one(const PreintParams& p, int grid, int block, cudaStream_t st) {
@@ -1060,6 +1303,11 @@ cudaError_t preint_launch(int model, int dtype, int flags, const PreintParams& p
     PreintParams p = p0;
     if (p.n_windows == 0) return cudaSuccess;
     if (max_smem_bytes < 232448) return cudaErrorInvalidConfiguration;
+    static const bool force_fused = getenv("CPI_B200_FUSED") != nullptr;
+    if (model == 1 && !(flags & CPI_FLAG_IMU_AVG) && !force_fused && p.n_windows < (int64_t)2147483647) {
+        if (launches) *launches = 1;
+        return dtype == 32 ? launch_ws<float>(p, num_sms, st) : launch_ws<double>(p, num_sms, st);
+    }
     p.wpb = preint_pick_wpb(model, dtype, p.n_windows, num_sms);
     const int block = (p.wpb + 31) / 32 * 32;
     const int grid = (int)((p.n_windows + p.wpb - 1) / p.wpb);
