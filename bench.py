@@ -38,6 +38,8 @@ WORKLOADS = {
                         desc="configs[2]: 100k-window batch x 400 samples, CPI v2, fp64"),
 }
 DFMA_PEAK_TFLOPS = 34.17   # measured on this pool's B200 by tools/microbench.cu (profiles/microbench_r01.jsonl), burst == sustained
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/*.txt)
+NCU_TRAFFIC_BYTES = {"v1_10k_200": 113.78e6 + 3.72e6}
 
 
 def measured_peaks():
@@ -253,8 +255,9 @@ def main():
                "gpu_launches": int(launches),
                "kernel_ms": kern_ms,
                "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": DFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach_tf / DFMA_PEAK_TFLOPS,
-                            "traffic": None,
-                            "note": "fp64 CUDA-core (DFMA) bound, not HBM/tensor: 85 flop/B; peak = DFMA microbenchmark measured on this pool "
+                            "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
+                            "note": "fp64 CUDA-core (DFMA) bound, not HBM/tensor: 85 flop/B; traffic = DRAM bytes/launch from profiles/r01_k1_ws.txt (algorithmic 136 MB, "
+                                    "the 23 MB of records mostly stay in L2); peak = DFMA microbenchmark measured on this pool "
                                     "(tools/microbench.cu, profiles/microbench_r01.jsonl); achieved = algorithmic flops (5.8 kflop/sample v1, 15 v2) / kernel time",
                             "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"], "peak_source": how}},
                "clocks": clocks}

@@ -1,5 +1,6 @@
 // extern "C" boundary of libcpi_b200.so (declared in include/cpi_b200.h).  Plain pointers and sizes only.
 #include <atomic>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -44,9 +45,11 @@ int device_info(DevInfo& d) {
 
 // grow-only scratch buffers for the *_host entry points (per process; guarded by one mutex: host calls serialise)
 struct Scratch {
+    static constexpr int NSTREAM = 4;
     void* dev[8] = {nullptr}; size_t dev_sz[8] = {0};
-    void* pin[4] = {nullptr}; size_t pin_sz[4] = {0};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;            // copy-in / general stream
+    cudaStream_t work[NSTREAM] = {nullptr};   // one per pipeline chunk (kernel + copy-out)
+    cudaEvent_t ev[NSTREAM] = {nullptr};
     int device = -1;
 };
 std::mutex g_scratch_mu;
@@ -59,9 +62,17 @@ int scratch_prepare() {
         // buffers belong to the device they were allocated on; drop them if the caller switched device
         for (int i = 0; i < 8; i++) { if (g_scratch.dev[i]) cudaFree(g_scratch.dev[i]); g_scratch.dev[i] = nullptr; g_scratch.dev_sz[i] = 0; }
         if (g_scratch.stream) { cudaStreamDestroy(g_scratch.stream); g_scratch.stream = nullptr; }
+        for (int i = 0; i < Scratch::NSTREAM; i++) {
+            if (g_scratch.work[i]) { cudaStreamDestroy(g_scratch.work[i]); g_scratch.work[i] = nullptr; }
+            if (g_scratch.ev[i]) { cudaEventDestroy(g_scratch.ev[i]); g_scratch.ev[i] = nullptr; }
+        }
         g_scratch.device = dev;
     }
     if (!g_scratch.stream) CU(cudaStreamCreateWithFlags(&g_scratch.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < Scratch::NSTREAM; i++) {
+        if (!g_scratch.work[i]) CU(cudaStreamCreateWithFlags(&g_scratch.work[i], cudaStreamNonBlocking));
+        if (!g_scratch.ev[i]) CU(cudaEventCreateWithFlags(&g_scratch.ev[i], cudaEventDisableTiming));
+    }
     return CPI_OK;
 }
 int dev_buf(int slot, size_t bytes, void** out) {
@@ -74,6 +85,29 @@ int dev_buf(int slot, size_t bytes, void** out) {
         g_scratch.dev_sz[slot] = bytes;
     }
     *out = g_scratch.dev[slot];
+    return CPI_OK;
+}
+
+int preintegrate_dev(int model, int dtype, int64_t n_windows, const int64_t* sample_offsets, int64_t ns_uniform,
+                            const void* samples, const void* lin, const double* sigmas, int flags, void* out_records, void* stream, int wpb) {
+    if (model != 1 && model != 2) return fail(CPI_EINVAL, "model must be 1 or 2 (got %d)", model);
+    if (dtype != 64 && dtype != 32) return fail(CPI_EINVAL, "dtype must be 64 or 32 (got %d)", dtype);
+    if (n_windows < 0 || (!sample_offsets && ns_uniform < 0)) return fail(CPI_EINVAL, "negative count");
+    if (n_windows == 0) return CPI_OK;
+    if (!lin || !sigmas || !out_records) return fail(CPI_EINVAL, "null pointer argument");
+    if (!samples && (sample_offsets || ns_uniform > 0)) return fail(CPI_EINVAL, "samples is null");
+    if (model == 1 && (flags & CPI_FLAG_ANALYTIC_JACOBIANS)) flags &= ~CPI_FLAG_ANALYTIC_JACOBIANS;   // model 1 is always analytic
+    DevInfo d;
+    int rc = device_info(d);
+    if (rc) return rc;
+    cpi::PreintParams p;
+    p.n_windows = n_windows; p.offsets = sample_offsets; p.ns_uniform = ns_uniform;
+    p.samples = samples; p.lin = lin; p.out = out_records;
+    p.q_w = sigmas[0] * sigmas[0]; p.q_wb = sigmas[1] * sigmas[1]; p.q_a = sigmas[2] * sigmas[2]; p.q_ab = sigmas[3] * sigmas[3];
+    p.wpb = wpb;
+    int launches = 0;
+    CU(cpi::preint_launch(model, dtype, flags, p, d.sms, d.max_smem, (cudaStream_t)stream, &launches));
+    g_launches += launches;
     return CPI_OK;
 }
 
@@ -100,25 +134,7 @@ int cpi_device_count(void) {
 
 int cpi_preintegrate_batch(int model, int dtype, int64_t n_windows, const int64_t* sample_offsets, int64_t ns_uniform,
                            const void* samples, const void* lin, const double* sigmas, int flags, void* out_records, void* stream) {
-    if (model != 1 && model != 2) return fail(CPI_EINVAL, "model must be 1 or 2 (got %d)", model);
-    if (dtype != 64 && dtype != 32) return fail(CPI_EINVAL, "dtype must be 64 or 32 (got %d)", dtype);
-    if (n_windows < 0 || (!sample_offsets && ns_uniform < 0)) return fail(CPI_EINVAL, "negative count");
-    if (n_windows == 0) return CPI_OK;
-    if (!lin || !sigmas || !out_records) return fail(CPI_EINVAL, "null pointer argument");
-    if (!samples && (sample_offsets || ns_uniform > 0)) return fail(CPI_EINVAL, "samples is null");
-    if (model == 1 && (flags & CPI_FLAG_ANALYTIC_JACOBIANS)) flags &= ~CPI_FLAG_ANALYTIC_JACOBIANS;   // model 1 is always analytic
-    DevInfo d;
-    int rc = device_info(d);
-    if (rc) return rc;
-    cpi::PreintParams p;
-    p.n_windows = n_windows; p.offsets = sample_offsets; p.ns_uniform = ns_uniform;
-    p.samples = samples; p.lin = lin; p.out = out_records;
-    p.q_w = sigmas[0] * sigmas[0]; p.q_wb = sigmas[1] * sigmas[1]; p.q_a = sigmas[2] * sigmas[2]; p.q_ab = sigmas[3] * sigmas[3];
-    p.wpb = 0;
-    int launches = 0;
-    CU(cpi::preint_launch(model, dtype, flags, p, d.sms, d.max_smem, (cudaStream_t)stream, &launches));
-    g_launches += launches;
-    return CPI_OK;
+    return preintegrate_dev(model, dtype, n_windows, sample_offsets, ns_uniform, samples, lin, sigmas, flags, out_records, stream, 0);
 }
 
 int cpi_preintegrate_batch_host(int model, int dtype, int64_t n_windows, const int64_t* sample_offsets, int64_t ns_uniform,
@@ -129,28 +145,61 @@ int cpi_preintegrate_batch_host(int model, int dtype, int64_t n_windows, const i
     if (n_windows == 0) return CPI_OK;
     if (!lin || !sigmas || !out_records) return fail(CPI_EINVAL, "null pointer argument");
     const int avg = (flags & CPI_FLAG_IMU_AVG) ? 1 : 0;
-    const int64_t entries = sample_offsets ? sample_offsets[n_windows] : n_windows * (ns_uniform + avg);
+    const int64_t ent_w = ns_uniform + avg;
+    const int64_t entries = sample_offsets ? sample_offsets[n_windows] : n_windows * ent_w;
     if (entries > 0 && !samples) return fail(CPI_EINVAL, "samples is null");
     const int rd = cpi_record_doubles(model);
-    std::lock_guard<std::mutex> lk(g_scratch_mu);
-    int rc = scratch_prepare();
-    if (rc) return rc;
-    cudaStream_t st = g_scratch.stream;
-    void *d_s, *d_l, *d_o, *d_off = nullptr;
     const size_t es = dtype == 32 ? 4 : 8;
+    DevInfo d;
+    int rc = device_info(d);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    if ((rc = scratch_prepare())) return rc;
+    void *d_s, *d_l, *d_o, *d_off = nullptr;
     if ((rc = dev_buf(0, (size_t)entries * CPI_SAMPLE_DOUBLES * es + 16, &d_s))) return rc;
     if ((rc = dev_buf(1, (size_t)n_windows * CPI_LIN_DOUBLES * es, &d_l))) return rc;
     if ((rc = dev_buf(2, (size_t)n_windows * rd * es, &d_o))) return rc;
-    if (sample_offsets) {
-        if ((rc = dev_buf(3, (size_t)(n_windows + 1) * 8, &d_off))) return rc;
-        CU(cudaMemcpyAsync(d_off, sample_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (sample_offsets && (rc = dev_buf(3, (size_t)(n_windows + 1) * 8, &d_off))) return rc;
+
+    // Chunked pipeline: H2D of chunk k+1 runs under the kernel of chunk k, D2H of chunk k under the kernel of chunk k+1.
+    // The kernel is latency-bound on small grids, so every chunk is launched with the windows-per-block the
+    // WHOLE batch would use: a chunk then occupies only its share of the SMs and the chunk kernels run concurrently on
+    // separate streams instead of serialising.
+    const size_t in_bytes = (size_t)entries * CPI_SAMPLE_DOUBLES * es;
+    int nchunk = 1;
+    if (in_bytes >= ((size_t)24 << 20) && n_windows >= 8 * (int64_t)d.sms) nchunk = Scratch::NSTREAM;
+    if (const char* e = getenv("CPI_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= Scratch::NSTREAM) nchunk = v; }   // A/B measurements
+    const int cap = (model == 1 && !avg) ? cpi::preint_ws_cap(dtype) : cpi::preint_pick_wpb(model, dtype, (int64_t)1 << 40, d.sms);
+    int64_t need = (n_windows + d.sms - 1) / d.sms;
+    const int wpb = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+    const int64_t blocks = (n_windows + wpb - 1) / wpb;
+    const int64_t blocks_per_chunk = (blocks + nchunk - 1) / nchunk;
+
+    cudaStream_t s_in = g_scratch.stream;
+    if (sample_offsets) CU(cudaMemcpyAsync(d_off, sample_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, s_in));
+    for (int k = 0; k < nchunk; k++) {
+        const int64_t lo = (int64_t)k * blocks_per_chunk * wpb;
+        if (lo >= n_windows) break;
+        const int64_t hi = (lo + blocks_per_chunk * wpb < n_windows) ? lo + blocks_per_chunk * wpb : n_windows;
+        const int64_t e_lo = sample_offsets ? sample_offsets[lo] : lo * ent_w, e_hi = sample_offsets ? sample_offsets[hi] : hi * ent_w;
+        cudaStream_t sk = g_scratch.work[k];
+        CU(cudaMemcpyAsync((char*)d_l + (size_t)lo * CPI_LIN_DOUBLES * es, (const char*)lin + (size_t)lo * CPI_LIN_DOUBLES * es,
+                           (size_t)(hi - lo) * CPI_LIN_DOUBLES * es, cudaMemcpyHostToDevice, s_in));
+        if (e_hi > e_lo)
+            CU(cudaMemcpyAsync((char*)d_s + (size_t)e_lo * CPI_SAMPLE_DOUBLES * es, (const char*)samples + (size_t)e_lo * CPI_SAMPLE_DOUBLES * es,
+                               (size_t)(e_hi - e_lo) * CPI_SAMPLE_DOUBLES * es, cudaMemcpyHostToDevice, s_in));
+        CU(cudaEventRecord(g_scratch.ev[k], s_in));
+        CU(cudaStreamWaitEvent(sk, g_scratch.ev[k], 0));
+        // offsets are absolute entry indices, so CSR chunks keep the global sample base; uniform chunks shift it
+        const void* s_base = sample_offsets ? d_s : (const void*)((const char*)d_s + (size_t)e_lo * CPI_SAMPLE_DOUBLES * es);
+        rc = preintegrate_dev(model, dtype, hi - lo, sample_offsets ? (const int64_t*)d_off + lo : nullptr, ns_uniform, s_base,
+                              (const char*)d_l + (size_t)lo * CPI_LIN_DOUBLES * es, sigmas, flags, (char*)d_o + (size_t)lo * rd * es, sk, wpb);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync((char*)out_records + (size_t)lo * rd * es, (const char*)d_o + (size_t)lo * rd * es, (size_t)(hi - lo) * rd * es,
+                           cudaMemcpyDeviceToHost, sk));
     }
-    CU(cudaMemcpyAsync(d_l, lin, (size_t)n_windows * CPI_LIN_DOUBLES * es, cudaMemcpyHostToDevice, st));
-    if (entries > 0) CU(cudaMemcpyAsync(d_s, samples, (size_t)entries * CPI_SAMPLE_DOUBLES * es, cudaMemcpyHostToDevice, st));
-    rc = cpi_preintegrate_batch(model, dtype, n_windows, (const int64_t*)d_off, ns_uniform, d_s, d_l, sigmas, flags, d_o, st);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(out_records, d_o, (size_t)n_windows * rd * es, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    for (int k = 0; k < nchunk; k++) CU(cudaStreamSynchronize(g_scratch.work[k]));
+    CU(cudaStreamSynchronize(s_in));
     return CPI_OK;
 }
 

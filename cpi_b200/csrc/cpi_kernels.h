@@ -13,7 +13,7 @@ struct PreintParams {
     const void* lin;          // device
     void* out;                // device
     double q_w, q_wb, q_a, q_ab;   // sigma^2  (CpiBase.h:54-57)
-    int wpb;                  // windows per block == shared-memory window stride (chosen by preint_launch)
+    int wpb;                  // windows per block; 0 on entry = let preint_launch choose (one wave if possible)
 };
 
 struct FactorParams {
@@ -29,6 +29,7 @@ struct FactorParams {
 };
 
 int preint_pick_wpb(int model, int dtype, int64_t n_windows, int num_sms);
+int preint_ws_cap(int dtype);
 cudaError_t preint_launch(int model, int dtype, int flags, const PreintParams& p0, int num_sms, int max_smem_bytes, cudaStream_t st, int* launches);
 cudaError_t factor_launch(int model, const FactorParams& p, cudaStream_t st);
 cudaError_t predict_launch(int model, int64_t n, const double* states, const double* records, const double* lin, double* out, cudaStream_t st);

@@ -751,7 +751,8 @@ template <class T> struct Fetch {
     const T* sp; const T* buf; uint32_t buf0, bar0; int shift; int64_t n_tma;
     CPI_DEV void init(const T* sp_, int64_t o0, int64_t nsteps, const T* buf_, uint32_t bar0_) {
         sp = sp_; buf = buf_; buf0 = smem_u32(buf_); bar0 = bar0_;
-        shift = (int)((7 * o0) % EPL);
+        shift = (int)(((uintptr_t)sp_ & 15) / sizeof(T));      // misalignment of the window start w.r.t. 16 bytes, in elements
+        (void)o0;
         n_tma = nsteps > 0 ? (nsteps - 1) / CH : 0;
         mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -793,7 +794,6 @@ template <int MODEL, bool AVG, bool ANALYTIC, class T>
 __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
     using TL = Tile<MODEL, T>;
     constexpr int S = TL::S;
-    constexpr int EPL = 16 / (int)sizeof(T);             // elements per 16 bytes
     constexpr int CH = 8 / (int)sizeof(T) * 2;           // samples per TMA chunk: 2 (fp64, 2 x 56 B) or 4 (fp32, 4 x 28 B) = 112 B
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
@@ -825,7 +825,7 @@ __global__ void __launch_bounds__(128, 1) k_preintegrate(const PreintParams p) {
     const T* sp = reinterpret_cast<const T*>(p.samples) + o0 * CPI_SAMPLE_DOUBLES;
 
     // ---- TMA pipeline set-up
-    const int shift = (int)((7 * o0) % EPL);             // misalignment of the window start w.r.t. 16 bytes, in elements
+    const int shift = (int)(((uintptr_t)sp & 15) / sizeof(T));   // misalignment of the window start w.r.t. 16 bytes, in elements
     const int64_t n_tma = AVG ? 0 : (nsteps > 0 ? (nsteps - 1) / CH : 0);   // chunks with at least one more sample after them
     if (!AVG) {
         mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
@@ -1258,7 +1258,7 @@ static cudaError_t launch_ws(const PreintParams& p0, int num_sms, cudaStream_t s
     }
     const int cap = TileWS<T>::S;
     const int64_t need = (p.n_windows + num_sms - 1) / num_sms;
-    p.wpb = (int)(need <= cap ? (need < 1 ? 1 : need) : cap);
+    if (p.wpb <= 0 || p.wpb > cap) p.wpb = (int)(need <= cap ? (need < 1 ? 1 : need) : cap);   // p0.wpb > 0: caller-chosen (chunked host path)
     const int block = 2 * ((p.wpb + 31) / 32 * 32);
     const int grid = (int)((p.n_windows + p.wpb - 1) / p.wpb);
     kern<<<grid, block, TileWS<T>::bytes, st>>>(p);
@@ -1291,6 +1291,8 @@ int preint_pick_wpb(int model, int dtype, int64_t n_windows, int num_sms) {
     return cap;
 }
 
+int preint_ws_cap(int dtype) { return dtype == 32 ? TileWS<float>::S : TileWS<double>::S; }
+
 template <class T>
 static cudaError_t launch_typed(int model, int flags, const PreintParams& p, int grid, int block, cudaStream_t st) {
     const bool avg = flags & CPI_FLAG_IMU_AVG, ana = flags & CPI_FLAG_ANALYTIC_JACOBIANS;
@@ -1308,7 +1310,8 @@ cudaError_t preint_launch(int model, int dtype, int flags, const PreintParams& p
         if (launches) *launches = 1;
         return dtype == 32 ? launch_ws<float>(p, num_sms, st) : launch_ws<double>(p, num_sms, st);
     }
-    p.wpb = preint_pick_wpb(model, dtype, p.n_windows, num_sms);
+    { const int cap = preint_pick_wpb(model, dtype, (int64_t)1 << 40, num_sms);
+      if (p.wpb <= 0 || p.wpb > cap) p.wpb = preint_pick_wpb(model, dtype, p.n_windows, num_sms); }
     const int block = (p.wpb + 31) / 32 * 32;
     const int grid = (int)((p.n_windows + p.wpb - 1) / p.wpb);
     cudaError_t e = dtype == 32 ? launch_typed<float>(model, flags, p, grid, block, st) : launch_typed<double>(model, flags, p, grid, block, st);
