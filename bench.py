@@ -36,7 +36,17 @@ WORKLOADS = {
                        desc="configs[1]: 10k-window batch x 200 samples, CPI v1 mean+covariance, fp64"),
     "v2_100k_400": dict(model=2, n=100_000, ns=400, rate=400.0, flops_per_sample=15.0e3, bytes_per_window=24_968,
                         desc="configs[2]: 100k-window batch x 400 samples, CPI v2, fp64"),
+    # configs[0]: the reference's own CPU-runnable case (one window, 100 samples); for the GPU arm this is pure launch latency
+    "v1_single_100": dict(model=1, n=1, ns=100, rate=200.0, flops_per_sample=5.8e3, bytes_per_window=8_024, single=True,
+                          desc="configs[0]: single CPI v1 window, 100 IMU samples @ 200 Hz, fp64"),
+    # configs[3] is quoted on 8 GPUs: 1M windows = 125k per GPU (weak-scaling unit); fp32-storage variant
+    "v1_1m_200_fp32": dict(model=1, n=125_000, ns=200, rate=200.0, flops_per_sample=5.8e3, bytes_per_window=6_812, fp32=True,
+                           desc="configs[3]: 1M-window batch x 200 samples, CPI v1, fp32 storage, 125k windows per GPU + NCCL all-gather"),
+    # configs[4]: the factor-evaluation kernel K3 over a 5k-keyframe chain (factors/s, HBM-write bound)
+    "factor_5k": dict(model=1, n=4_999, ns=20, rate=200.0, factor=True,
+                      desc="configs[4]: 5k-keyframe chain, batched ImuFactorCPIv1 residual + H1 + H2 (4 999 factors per step)"),
 }
+FFMA_PEAK_TFLOPS = 72.51   # same microbenchmark, fp32 FFMA
 DFMA_PEAK_TFLOPS = 34.17   # measured on this pool's B200 by tools/microbench.cu (profiles/microbench_r01.jsonl), burst == sustained
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/*.txt)
 NCU_TRAFFIC_BYTES = {"v1_10k_200": 113.78e6 + 3.72e6}
@@ -115,6 +125,22 @@ def run_reference(args, wl):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    if wl.get("single"):
+        # one window, reference CpiV1 on ONE thread, median of >= 1000 repeats
+        from oracle.oracle import Oracle, Reference
+        from cpi_b200 import synth
+        impl, kind = (Reference(), "reference") if Reference.available() else (Oracle(), "port")
+        S, L = synth.make_windows(1, wl["ns"], rate=wl["rate"], special=False)
+        ts = []
+        for _ in range(1200):
+            t0 = time.perf_counter(); impl.preintegrate(wl["model"], S, L, synth.SIGMAS, 0, ns=wl["ns"], nthreads=1); ts.append(time.perf_counter() - t0)
+        ms = 1e3 * float(np.median(ts[200:]))
+        print(json.dumps({"impl": "reference", "metric": "imu_windows_per_sec", "value": 1e3 / ms, "unit": "windows/s", "n_gpus": args.gpus, "steps": 1000, "warmup": 200,
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": wl["desc"], "windows_per_step": 1, "samples_per_window": wl["ns"], "model": "CpiV1"},
+                          "cpu_baseline": {"value": 1e3 / ms, "unit": "windows/s", "cores": 1, "kind": kind, "sample": "1 window x 100 samples, median of 1000 repeats (includes ~3 us of ctypes call overhead)"},
+                          "e2e": {"value": 1e3 / ms, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
     # bounded sample: calibrate on a small run, then size each step for ~5 s of CPU work (all host threads)
     v0, kind, cores, _ = cpu_arm(wl, max(2 * cores, 64))
     sample = int(min(wl["n"], max(cores, v0 * 5.0)))
@@ -134,6 +160,87 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def run_factor(args, wl):
+    """configs[4]: K3 (ImuFactorCPIv1::evaluateError batched) over a 5k-keyframe chain.  HBM-write bound: 4 496 algorithmic
+    bytes per factor (776 in, 3 720 out); at 5k factors the launch is ~10 us, i.e. launch-latency sized."""
+    from cpi_b200 import synth
+    from oracle.oracle import Oracle, Reference
+    model, n, ns = wl["model"], wl["n"], wl["ns"]
+    S, L = synth.make_windows(n, ns, rate=wl["rate"], first_window=9000)
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        impl, kind = (Reference(), "reference") if Reference.available() else (Oracle(), "port")
+        cores = os.cpu_count() or 1
+        rec = impl.preintegrate(model, S, L, synth.SIGMAS, 0, ns=ns, nthreads=cores)
+        X = synth.make_states(rec, L, model)
+        ts = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter(); impl.factor_eval(model, X, rec, L, nthreads=cores); ts.append(time.perf_counter() - t0)
+        ms = 1e3 * float(np.mean(ts[args.warmup:])); v = n / (ms * 1e-3)
+        print(json.dumps({"impl": "reference", "metric": "imu_factors_per_sec", "value": v, "unit": "factors/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": wl["desc"]}, "cpu_baseline": {"value": v, "unit": "factors/s", "cores": cores, "kind": kind, "sample": f"{n} factors per step"},
+                          "e2e": {"value": v, "unit": "factors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    import torch
+    from cpi_b200 import capi, factor, preint
+    torch.cuda.set_device(0)
+    lib = capi.load()
+    rec = preint.preintegrate_host(model, S, L, synth.SIGMAS, 0, ns=ns)
+    X = synth.make_states(rec, L, model)
+    dX, dR, dL = (torch.from_numpy(a).cuda() for a in (X, rec, L))
+    outs = (torch.empty((n, 15), dtype=torch.float64, device="cuda"), torch.empty((n, 225), dtype=torch.float64, device="cuda"),
+            torch.empty((n, 225), dtype=torch.float64, device="cuda"))
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2: written between timed launches
+    stream = torch.cuda.current_stream()
+    t_settle = time.perf_counter()
+    while time.perf_counter() - t_settle < 0.15:
+        factor.factor_eval(model, dX, dR, dL, out=outs); torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.warmup):
+        flush.zero_(); factor.factor_eval(model, dX, dR, dL, out=outs)
+    launches0 = capi.launch_count()
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        flush.zero_()                                                       # L2 flush, outside the per-launch event pair
+        evs[i][0].record(stream); factor.factor_eval(model, dX, dR, dL, out=outs); evs[i][1].record(stream)
+    torch.cuda.synchronize()
+    launches = capi.launch_count() - launches0
+    ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    peaks, how = measured_peaks()
+    ach = 4496.0 * n / (ms * 1e-3) * 1e-9
+    hX, hR, hL = (torch.from_numpy(a).pin_memory() for a in (X, rec, L))
+    hE, hH1, hH2 = (torch.empty(sh, dtype=torch.float64).pin_memory() for sh in ((n, 15), (n, 225), (n, 225)))
+    import ctypes
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    def host_step():
+        capi.check(lib.cpi_imu_factor_eval_batch_host(model, n, n + 1, P(hX), None, None, P(hR), P(hL), P(hE), P(hH1), P(hH2)))
+    for _ in range(3):
+        host_step()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        host_step()
+    e2e_ms = (time.perf_counter() - t0) * 100.0
+    out = {"metric": "imu_factors_per_sec", "value": n / (ms * 1e-3), "unit": "factors/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": wl["desc"], "l2": "192 MB buffer written between timed launches (outside the event pair)"}, "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                        "note": "4 496 algorithmic B/factor; at 5k factors (22 MB) the launch is latency-sized: 22 MB at peak would take 3.4 us"},
+           "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "factors/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int((hX.numel() + hR.numel() + hL.numel()) * 8),
+                   "d2h_bytes_per_step": int((hE.numel() + hH1.numel() + hH2.numel()) * 8), "api": "cpi_imu_factor_eval_batch_host"}}
+    if not args.no_cpu_baseline:
+        impl, kind = (Reference(), "reference") if Reference.available() else (Oracle(), "port")
+        cores = os.cpu_count() or 1
+        impl.factor_eval(model, X, rec, L, nthreads=cores)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            impl.factor_eval(model, X, rec, L, nthreads=cores)
+        dt = (time.perf_counter() - t0) / 5
+        out["cpu_baseline"] = {"value": n / dt, "unit": "factors/s", "cores": cores, "kind": kind, "sample": f"{n} factors x 5 repeats, reference evaluateError with H1 and H2"}
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -147,6 +254,8 @@ def main():
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if wl.get("factor"):
+        return run_factor(args, wl)
     if args.impl == "reference":
         return run_reference(args, wl)
 
@@ -167,18 +276,20 @@ def main():
     dev = torch.device("cuda", torch.cuda.current_device())
     model, n, ns = wl["model"], wl["n"], wl["ns"]
     rd = capi.REC_DOUBLES[model]
+    f32 = bool(wl.get("fp32"))
+    tdt, es = (torch.float32, 4) if f32 else (torch.float64, 8)
 
     # ---- resident inputs: NB distinct batches, NB * bytes > L2
-    bytes_in = n * ns * 56 + n * 104
-    NB = max(2, int(np.ceil(300e6 / bytes_in)))
+    bytes_in = n * ns * 7 * es + n * 13 * es
+    NB = min(8, max(2, int(np.ceil(300e6 / bytes_in))))
     if bytes_in > 300e6:
         NB = 2
     batches = []
     for b in range(NB):
         S, L = synth.make_windows(n, ns, rate=wl["rate"], first_window=(rank * NB + b) * n)
-        batches.append((torch.from_numpy(S).to(dev), torch.from_numpy(L).to(dev)))
+        batches.append((torch.from_numpy(S).to(tdt).to(dev), torch.from_numpy(L).to(tdt).to(dev)))
     del S, L      # NB: dropping a 112 MB numpy array is a ~12 ms munmap on the host -- must not happen inside the timed loop
-    gather = torch.empty((world, n, rd), dtype=torch.float64, device=dev)     # rank r's kernel writes gather[r] in place
+    gather = torch.empty((world, n, rd), dtype=tdt, device=dev)     # rank r's kernel writes gather[r] in place
     mine = gather[rank]
     stream = torch.cuda.current_stream()
 
@@ -248,31 +359,34 @@ def main():
         ach_tf = flops / (kern_ms * 1e-3) * 1e-12
         ach_gbs = wl["bytes_per_window"] * n / (kern_ms * 1e-3) * 1e-9
         out = {"metric": "imu_windows_per_sec", "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32 storage + f32 covariance RK4, f64 rotations/coefficients/means" if f32 else "f64", "data": "synthetic",
                "config": {"workload": wl["desc"], "windows_per_gpu": n, "samples_per_window": ns, "model": f"CpiV{model}",
                           "parallelism": f"window-sharded x{world}" + (", one NCCL all-gather of records per step" if world > 1 else ""),
                           "l2": f"{NB} rotating resident input batches = {NB * bytes_in / 1e6:.0f} MB > 126 MB L2"},
                "gpu_launches": int(launches),
                "kernel_ms": kern_ms,
-               "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": DFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach_tf / DFMA_PEAK_TFLOPS,
+               "roofline": {"bound": "fp32+fp64 CUDA cores" if f32 else "fp64", "achieved": ach_tf, "peak": FFMA_PEAK_TFLOPS if f32 else DFMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                            "frac": ach_tf / (FFMA_PEAK_TFLOPS if f32 else DFMA_PEAK_TFLOPS),
                             "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
-                            "note": "fp64 CUDA-core (DFMA) bound, not HBM/tensor: 85 flop/B; traffic = DRAM bytes/launch from profiles/r01_k1_ws.txt (algorithmic 136 MB, "
-                                    "the 23 MB of records mostly stay in L2); peak = DFMA microbenchmark measured on this pool "
-                                    "(tools/microbench.cu, profiles/microbench_r01.jsonl); achieved = algorithmic flops (5.8 kflop/sample v1, 15 v2) / kernel time",
+                            "note": "CUDA-core FMA bound, not HBM/tensor (85 flop/B); peak = DFMA / FFMA microbenchmark measured on this pool (tools/microbench.cu, "
+                                    "profiles/microbench_r01.jsonl); achieved = algorithmic flops (5.8 kflop/sample v1, 15 v2; SURVEY 8d) / CUDA-event kernel time; "
+                                    "traffic = DRAM bytes per launch from the committed ncu capture (profiles/r01_k1_ws.txt) where one exists for this workload",
                             "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"], "peak_source": how}},
                "clocks": clocks}
 
     # ---- e2e through the C-ABI host entry point, pinned host buffers, H2D + kernel + D2H inside the timed region
     if not args.no_e2e:
         S, L = synth.make_windows(n, ns, rate=wl["rate"], first_window=rank * n)
-        hS = torch.from_numpy(S).pin_memory(); hL = torch.from_numpy(L).pin_memory()
-        hO = torch.empty((n, rd), dtype=torch.float64).pin_memory()
+        hS = torch.from_numpy(S).to(tdt).pin_memory(); hL = torch.from_numpy(L).to(tdt).pin_memory()
+        hO = torch.empty((n, rd), dtype=tdt).pin_memory()
+        del S, L
         sig = np.ascontiguousarray(synth.SIGMAS)
         lib = capi.load()
         import ctypes
 
         def host_step():
-            capi.check(lib.cpi_preintegrate_batch_host(model, 64, n, None, ns, ctypes.c_void_p(hS.data_ptr()), ctypes.c_void_p(hL.data_ptr()),
+            capi.check(lib.cpi_preintegrate_batch_host(model, 8 * es, n, None, ns, ctypes.c_void_p(hS.data_ptr()), ctypes.c_void_p(hL.data_ptr()),
                                                        ctypes.c_void_p(sig.ctypes.data), 0, ctypes.c_void_p(hO.data_ptr())))
         for _ in range(3):
             host_step()
@@ -291,7 +405,7 @@ def main():
             e2e_ms = float(t.item())
         if rank == 0:
             out["e2e"] = {"value": world * n / (e2e_ms * 1e-3), "unit": "windows/s", "ms_per_step": e2e_ms,
-                          "h2d_bytes_per_step": int(hS.numel() * 8 + hL.numel() * 8), "d2h_bytes_per_step": int(hO.numel() * 8),
+                          "h2d_bytes_per_step": int(hS.numel() * es + hL.numel() * es), "d2h_bytes_per_step": int(hO.numel() * es),
                           "api": "cpi_preintegrate_batch_host (C ABI, pinned host buffers)"}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
