@@ -257,6 +257,20 @@ int cpi_imu_factor_eval_batch_host(int model, int64_t n_factors, int64_t n_state
     return CPI_OK;
 }
 
+int cpi_imu_factor_hessian_batch(int model, int64_t n_factors, const double* records, const double* e, const double* H1, const double* H2,
+                                 double* G11, double* G12, double* G22, double* g1, double* g2, double* f, void* stream) {
+    if (model != 1 && model != 2) return fail(CPI_EINVAL, "model must be 1 or 2 (got %d)", model);
+    if (n_factors < 0) return fail(CPI_EINVAL, "negative count");
+    if (n_factors == 0) return CPI_OK;
+    if (!records || !e || !H1 || !H2 || !G11 || !G12 || !G22 || !g1 || !g2 || !f) return fail(CPI_EINVAL, "null pointer argument");
+    DevInfo d;
+    int rc = device_info(d);
+    if (rc) return rc;
+    CU(cpi::hessian_launch(cpi_record_doubles(model), n_factors, records, e, H1, H2, G11, G12, G22, g1, g2, f, (cudaStream_t)stream));
+    g_launches += 1;
+    return CPI_OK;
+}
+
 int cpi_predict_state_batch(int model, int64_t n, const double* states_k, const double* records, const double* lin, double* states_k1, void* stream) {
     if (model != 1 && model != 2) return fail(CPI_EINVAL, "model must be 1 or 2 (got %d)", model);
     if (n < 0) return fail(CPI_EINVAL, "negative count");

@@ -33,6 +33,8 @@ int preint_ws_cap(int dtype);
 cudaError_t preint_launch(int model, int dtype, int flags, const PreintParams& p0, int num_sms, int max_smem_bytes, cudaStream_t st, int* launches);
 cudaError_t factor_launch(int model, const FactorParams& p, cudaStream_t st);
 cudaError_t predict_launch(int model, int64_t n, const double* states, const double* records, const double* lin, double* out, cudaStream_t st);
+cudaError_t hessian_launch(int rd, int64_t n, const double* records, const double* e, const double* H1, const double* H2,
+                           double* G11, double* G12, double* G22, double* g1, double* g2, double* f, cudaStream_t st);
 cudaError_t retract_launch(int64_t n, const double* states, const double* xi, double* out, cudaStream_t st);
 
 }  // namespace cpi

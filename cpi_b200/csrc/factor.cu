@@ -247,6 +247,78 @@ __global__ void k_retract(int64_t n, const double* states, const double* xi, dou
     for (int k = 0; k < 12; k++) o[4 + k] = x[4 + k] + d[3 + k];
 }
 
+// ---- information-form linearisation of the IMU factors ("next" row 1 of SURVEY.md 8f) -------------------------------------
+// What GTSAM does right after evaluateError: whiten with the factor's Gaussian noise model (noiseModel::Gaussian::Covariance(P_meas),
+// gtsam/ImuFactorCPIv1.h:82) and accumulate the normal equations.  With Sigma = L L^T and Y = L^-1 [H1 H2 e]:
+//     G_ij = H_i^T Sigma^-1 H_j = Y_i^T Y_j,   g_i = -H_i^T Sigma^-1 e = -Y_i^T y_e,   f = e^T Sigma^-1 e = y_e^T y_e
+// (the HessianFactor convention: G, g = A^T b with A = R H, b = -R e; independent of which square root R of Sigma^-1 is used).
+// One warp per factor: Cholesky of the 15x15 covariance in shared memory, then lane c forward-substitutes column c of the 31
+// right-hand sides, then lane c forms row c of Y^T Y from broadcast reads of Y.
+__global__ void __launch_bounds__(128) k_factor_hessian(int64_t n, int rd, const double* records, const double* e, const double* H1, const double* H2,
+                                                        double* G11, double* G12, double* G22, double* g1, double* g2, double* fq) {
+    __shared__ double sL[4][15 * 16];      // lower Cholesky factor, row-major with pitch 16
+    __shared__ double sY[4][15 * 32];      // Y, row i pitch 32
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t f = (int64_t)blockIdx.x * 4 + wib;
+    if (f >= n) return;
+    double* L = sL[wib];
+    double* Y = sY[wib];
+    const double* P = records + f * (int64_t)rd + CPI_REC_P;
+    for (int k = lane; k < 225; k += 32) { const int r = k % 15, c = k / 15; if (r >= c) L[r * 16 + c] = __ldg(P + k); }   // lower triangle (P symmetric)
+    __syncwarp();
+    // right-looking Cholesky; a non-positive pivot (covariance not positive definite, e.g. a zero-step window) gives NaN outputs
+    for (int k = 0; k < 15; k++) {
+        const double d = sqrt(L[k * 16 + k]);
+        __syncwarp();
+        if (lane == 0) L[k * 16 + k] = d;
+        if (lane > k && lane < 15) L[lane * 16 + k] = L[lane * 16 + k] / d;
+        __syncwarp();
+        // trailing update: pairs (i, j) with k < j <= i < 15 out of the 120 lower-triangle entries
+        for (int t = lane; t < 120; t += 32) {
+            int i = 0, acc = 0;
+            while (acc + i + 1 <= t) { acc += i + 1; i++; }      // t -> (i, j) in the lower triangle incl. diagonal
+            const int j = t - acc;
+            if (j > k && i > k) L[i * 16 + j] -= L[i * 16 + k] * L[j * 16 + k];
+        }
+        __syncwarp();
+    }
+    // forward substitution, one right-hand side per lane: columns of H1 (0..14), H2 (15..29), e (30)
+    double y[15];
+    if (lane < 31) {
+        const double* b = lane < 15 ? H1 + f * 225 + 15 * lane : (lane < 30 ? H2 + f * 225 + 15 * (lane - 15) : e + f * 15);
+#pragma unroll
+        for (int i = 0; i < 15; i++) {
+            double t = __ldg(b + i);
+#pragma unroll
+            for (int k = 0; k < i; k++) t = fma(-L[i * 16 + k], y[k], t);
+            y[i] = t / L[i * 16 + i];
+            Y[i * 32 + lane] = y[i];
+        }
+    }
+    __syncwarp();
+    if (lane < 31) {
+        double g[31];
+#pragma unroll
+        for (int c = 0; c < 31; c++) {
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < 15; i++) t = fma(y[i], Y[i * 32 + c], t);
+            g[c] = t;
+        }
+        if (lane < 15) {
+#pragma unroll
+            for (int r = 0; r < 15; r++) G11[f * 225 + r + 15 * lane] = g[r];                 // column `lane` of H1^T W H1
+        } else if (lane < 30) {
+#pragma unroll
+            for (int r = 0; r < 15; r++) { G12[f * 225 + r + 15 * (lane - 15)] = g[r]; G22[f * 225 + r + 15 * (lane - 15)] = g[15 + r]; }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 15; r++) { g1[f * 15 + r] = -g[r]; g2[f * 15 + r] = -g[15 + r]; }
+            fq[f] = g[30];
+        }
+    }
+}
+
 // ---- launchers -------------------------------------------------------------------------------------------------------
 cudaError_t factor_launch(int model, const FactorParams& p, cudaStream_t st) {
     if (p.n == 0) return cudaSuccess;
@@ -270,6 +342,13 @@ cudaError_t predict_launch(int model, int64_t n, const double* states, const dou
     const int grid = (int)((n + 127) / 128);
     if (model == 1) k_predict<1><<<grid, 128, 0, st>>>(n, states, records, lin, out);
     else k_predict<2><<<grid, 128, 0, st>>>(n, states, records, lin, out);
+    return cudaGetLastError();
+}
+
+cudaError_t hessian_launch(int rd, int64_t n, const double* records, const double* e, const double* H1, const double* H2,
+                           double* G11, double* G12, double* G22, double* g1, double* g2, double* f, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_factor_hessian<<<(int)((n + 3) / 4), 128, 0, st>>>(n, rd, records, e, H1, H2, G11, G12, G22, g1, g2, f);
     return cudaGetLastError();
 }
 

@@ -71,6 +71,27 @@ def factor_eval(model, states, records, lin, idx_i=None, idx_j=None, want_H1=Tru
     return e, H1, H2
 
 
+def factor_hessian(model, records, e, H1, H2, stream=None):
+    """Information-form linearisation (cpi_imu_factor_hessian_batch): returns (G11, G12, G22 [n,225 col-major], g1, g2 [n,15], f [n]).
+    Device tensors in/out, or numpy (staged through torch).  Parity vs GTSAM unpinned (GTSAM is not in the reference tree)."""
+    import torch
+
+    lib = capi.load()
+    host = isinstance(records, np.ndarray)
+    if host:
+        records, e, H1, H2 = (torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda() for a in (records, e, H1, H2))
+    n = records.numel() // REC_DOUBLES[model]
+    dev = records.device
+    G11, G12, G22 = (torch.empty((n, 225), dtype=torch.float64, device=dev) for _ in range(3))
+    g1, g2 = (torch.empty((n, 15), dtype=torch.float64, device=dev) for _ in range(2))
+    f = torch.empty((n,), dtype=torch.float64, device=dev)
+    st = stream if stream is not None else torch.cuda.current_stream()
+    capi.check(lib.cpi_imu_factor_hessian_batch(model, n, _tptr(records.contiguous()), _tptr(e.contiguous()), _tptr(H1.contiguous()), _tptr(H2.contiguous()),
+                                                _tptr(G11), _tptr(G12), _tptr(G22), _tptr(g1), _tptr(g2), _tptr(f), ctypes.c_void_p(st.cuda_stream)))
+    out = (G11, G12, G22, g1, g2, f)
+    return tuple(t.cpu().numpy() for t in out) if host else out
+
+
 def predict_state(model, states_k, records, lin, stream=None):
     """getpredictedstate_v1/_v2 (solvers/GraphSolver_IMU.cpp:263-307), batched.  Device tensors, or numpy (staged via torch)."""
     import torch

@@ -12,6 +12,7 @@
  *   cpi_imu_factor_eval_batch* replaces ImuFactorCPIv1::evaluateError (gtsam/ImuFactorCPIv1.cpp:37-208) and
  *                              ImuFactorCPIv2::evaluateError (gtsam/ImuFactorCPIv2.cpp:38-212): unwhitened 15-d
  *                              residual and the two 15x15 Jacobians, for many factors at once.
+ *   cpi_imu_factor_hessian_batch  the step GTSAM performs next: information-form blocks H^T P^-1 H, -H^T P^-1 e per factor.
  *   cpi_predict_state_batch*   replaces GraphSolver::getpredictedstate_v1/_v2 (solvers/GraphSolver_IMU.cpp:263-307).
  *   cpi_retract_batch*         replaces JPLNavState::retract (gtsam/JPLNavState.cpp:37-71).
  *
@@ -20,8 +21,9 @@
  * (cpi/CpiV1.h:277-281, gtsam/ImuFactorCPIv1.cpp:80-88).
  *
  * Functions without the _host suffix take DEVICE pointers and enqueue on `stream` (a cudaStream_t passed as
- * void*; NULL = legacy default stream) without synchronising.  *_host variants take HOST pointers, stage through
- * pinned buffers owned by the library, and return after the results are in the caller's buffers.
+ * void*; NULL = legacy default stream) without synchronising.  *_host variants take HOST pointers (pinned or pageable),
+ * copy through device buffers owned by the library -- big batches in a 4-deep H2D / kernel / D2H pipeline -- and return
+ * after the results are in the caller's buffers.
  * Every function returns CPI_OK (0) or a negative CPI_E* code; cpi_last_error() gives the message of the last
  * failure on the calling thread.  (The reference has no error convention for this path: feed_IMU returns void and
  * never checks its inputs -- CpiBase.h:86.)  No function falls back to a CPU implementation.
@@ -127,6 +129,19 @@ int cpi_imu_factor_eval_batch_host(int model, int64_t n_factors, int64_t n_state
                                    const double* states, const int64_t* idx_i, const int64_t* idx_j,
                                    const double* records, const double* lin,
                                    double* e, double* H1, double* H2);
+
+/*
+ * Information-form linearisation of n factors (device pointers), the step GTSAM performs right after evaluateError with
+ * the factor's noise model noiseModel::Gaussian::Covariance(P_meas) (gtsam/ImuFactorCPIv1.h:82, ImuFactorCPIv2.h:86):
+ *     G11 = H1^T P^-1 H1, G12 = H1^T P^-1 H2, G22 = H2^T P^-1 H2  (15x15 column-major each),
+ *     g1 = -H1^T P^-1 e, g2 = -H2^T P^-1 e  (15 each),  f = e^T P^-1 e      [HessianFactor convention: G, g = A^T b, f = b^T b]
+ * P = records[f].P_meas; e / H1 / H2 as produced by cpi_imu_factor_eval_batch.  A factor whose covariance is not positive
+ * definite (e.g. a zero-step window) gets NaN outputs (GTSAM throws there).  GTSAM itself is not in the reference tree
+ * (bitbucket gtborg/gtsam @ c21186c), so this entry point is validated against a dense CPU solve only: PARITY UNPINNED.
+ */
+int cpi_imu_factor_hessian_batch(int model, int64_t n_factors, const double* records,
+                                 const double* e, const double* H1, const double* H2,
+                                 double* G11, double* G12, double* G22, double* g1, double* g2, double* f, void* stream);
 
 /* ---- callers either side of the factor ("next" rows) ----------------------------------------------------------------- */
 
