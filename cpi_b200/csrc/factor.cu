@@ -12,7 +12,7 @@
 
 namespace cpi {
 
-constexpr int FPB = 32;                 // factors per block
+constexpr int FPB = 16;                 // factors per block (313 CTAs for a 5k chain: ~2 per SM, the launch is latency-sized)
 constexpr int FTILE = 15 + 225 + 225;   // doubles per factor in the staging tile
 
 
