@@ -5,8 +5,13 @@
 // (profiles/microbench_r01.jsonl): DFMA peak 34.2 TFLOP/s and a single warp per SMSP already reaches 90 % of it at
 // ILP >= 4, whereas every cross-lane double costs as much as 4 DFMA (SHFL / LDS bandwidth is 16 doubles/clk/SM vs 64
 // DFMA/clk/SM).  So the window recurrence is kept free of cross-lane traffic; the per-window state that does not fit
-// the register file -- the 90 unique non-trivial entries of the 15x15 covariance and its two RK4 work copies -- lives
-// in shared memory in [entry][window] order (conflict-free: lane == window).
+// the register file -- the 90 unique non-trivial entries of the 15x15 covariance (ping-pong copy), the RK4 stage values
+// other blocks depend on and the Jacobian state -- lives in shared memory in [entry][window] order (conflict-free:
+// lane == window; base + immediate addressing because the window stride is a compile-time constant).
+//
+// Two kernels share all device functions below: k_preintegrate (fused: one warp does everything for its 32 windows; used
+// for model 2, imu_avg, and large fp32 batches) and k_preintegrate_ws (warp-specialised, model 1: a FRONT warp and a
+// BACK warp per 32 windows, one sample apart).
 //
 // Arithmetic: the reference integrates  Pdot = F P + P F^T + G Qc G^T  with RK4, F evaluated at R_old / R_mid / R_mid /
 // R_new.  The same four stages are replicated here, but on the 3x3 block structure of F (five non-zero blocks), with P
@@ -17,7 +22,7 @@
 // Model 2's 21x21 system reduces to the same 15x15 tile plus three transient 3x3 blocks (clone rows c) per step: the
 // theta_klin rows/cols of P_big are identically zero and the clone rows are re-initialised from the theta rows every
 // step (B_k, CpiV2.h:436-443).  Its Jacobians are read out of the compounded transition Discrete_J_b; only 7 of its
-// 3x3 blocks are ever non-trivial in the 9 consumed columns, and Phi's RK4 has closed block forms (see phi_blocks()).
+// 3x3 blocks are ever non-trivial in the 9 consumed columns, and Phi's RK4 has closed block forms (the "Discrete_J_b" sections of k_preintegrate).
 #include <cstdlib>
 #include "cpi_common.cuh"
 #include "cpi_kernels.h"
