@@ -43,11 +43,6 @@ enum : int {
     PA = 75,  // P_p,ba         9
     PP = 84,  // P_p,p          sym 6
     NP = 90,  // P_bg,bg = pgg*I and P_ba,ba = paa*I are scalars in registers; P_theta,ba = P_bg,ba = 0 identically
-    // model 2 only, work copy only (transient clone rows, CpiV2.h state 15:18)
-    CT = 90,  // P_c,theta 9
-    CV = 99,  // P_c,v     9
-    CP = 108, // P_c,p     9
-    NCUR2 = 117,
     // model 2, default mode: the non-trivial blocks of Discrete_J_b in the consumed columns (bg, ba, theta_klin)
     D_TG = 0, D_VG = 9, D_PG = 18, D_VA = 27, D_PA = 36, D_VL = 45, D_PL = 54, ND = 63,
     // analytic Jacobian state (model 1; model 2 with CPI_FLAG_ANALYTIC_JACOBIANS): same 63-double region
