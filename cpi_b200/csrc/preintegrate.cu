@@ -1104,8 +1104,14 @@ __global__ void __launch_bounds__(256, 1) k_preintegrate_ws(const PreintParams p
     constexpr int S = TL::S;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nw = (p.wpb + 31) >> 5;                     // warps per role
-    const int role = threadIdx.x >= nw * 32;             // 0 = FRONT, 1 = BACK
-    const int tid = threadIdx.x - role * nw * 32;        // window lane within the CTA
+    // warp -> (role, pair).  Warp w issues from scheduler w % 4.  With 3 pairs (65..96 windows, the 10k-window case) six warps
+    // share four schedulers: give two of the critical BACK warps a scheduler of their own and double up FRONT warps
+    // (FRONT idles ~60 % of the time): schedulers {F0,F1} {F2,B2} {B0} {B1}.  Otherwise FRONT warps first, then BACK.
+    const int wid = threadIdx.x >> 5;
+    int role, pr;
+    if (nw == 3) { role = (0x2C >> wid) & 1; pr = (0x211020 >> (4 * wid)) & 15; }   // wid: 0 F0, 1 F2, 2 B0, 3 B1, 4 F1, 5 B2
+    else { role = wid >= nw; pr = wid - role * nw; }     // 0 = FRONT, 1 = BACK
+    const int tid = pr * 32 + (threadIdx.x & 31);         // window lane within the CTA
     const int64_t win = (int64_t)blockIdx.x * p.wpb + tid;
     const bool active = tid < p.wpb && win < p.n_windows;
 
