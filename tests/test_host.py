@@ -46,6 +46,11 @@ def test_argument_validation_without_gpu():
     rc = lib.cpi_preintegrate_batch(1, 64, -5, None, 1, None, None, None, 0, None, None)
     assert rc == -1
     assert lib.cpi_preintegrate_batch(1, 64, 0, None, 1, None, None, None, 0, None, None) == 0      # empty batch is a no-op
+    import numpy as np
+    bad = np.array([0, 5, 3, 9], dtype=np.int64); buf = np.zeros(64)
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)
+    rc = lib.cpi_preintegrate_batch_host(1, 64, 3, P(bad), 0, P(buf), P(buf), P(buf), 0, P(buf))
+    assert rc == -1 and b"non-decreasing" in lib.cpi_last_error()
     rc = lib.cpi_imu_factor_eval_batch(1, 4, None, None, None, None, None, None, None, None, None)
     assert rc == -1 and b"null" in lib.cpi_last_error()
 
