@@ -151,8 +151,8 @@ int cpi_preintegrate_batch_host(int model, int dtype, int64_t n_windows, const i
     if (sample_offsets) {                       // the host copy of the CSR layout can be validated before anything reaches the device
         if (sample_offsets[0] < 0) return fail(CPI_EINVAL, "sample_offsets[0] is negative");
         for (int64_t w = 0; w < n_windows; w++)
-            if (sample_offsets[w + 1] < sample_offsets[w] + avg)
-                return fail(CPI_EINVAL, "sample_offsets must be non-decreasing%s (window %lld)", avg ? " with at least the trailing imu_avg entry per window" : "", (long long)w);
+            if (sample_offsets[w + 1] < sample_offsets[w])     // an empty window is legal (also with imu_avg: it simply has no step)
+                return fail(CPI_EINVAL, "sample_offsets must be non-decreasing (window %lld)", (long long)w);
     } else if (ns_uniform < 0) return fail(CPI_EINVAL, "negative count");
     const int rd = cpi_record_doubles(model);
     const size_t es = dtype == 32 ? 4 : 8;
