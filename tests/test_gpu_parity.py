@@ -297,3 +297,13 @@ def test_factor_hessian_against_dense_cpu_solve(cuda, model):
     rec0 = rec[:4].copy(); rec0[1, 65:290] = 0.0
     out = factor.factor_hessian(model, rec0, e[:4], H1[:4], H2[:4])
     assert np.isnan(out[5][1]) and np.all(np.isfinite(out[5][[0, 2, 3]]))
+
+
+def test_sharded_entry_point_on_device(cuda):
+    """cpi_b200.shard.preintegrate_sharded with the real kernel (single process = world size 1; the N > 1 partition / padding /
+    all-gather logic is covered by the gloo tests in test_shard.py and by bench.py --gpus N)."""
+    from cpi_b200 import preint, shard
+    S, L = synth.make_windows(500, 40, first_window=2024)
+    got = shard.preintegrate_sharded(2, S.reshape(-1, 7), L, synth.SIGMAS, 0, ns=40)
+    cuda.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy(), preint.preintegrate_host(2, S, L, synth.SIGMAS, 0, ns=40))
