@@ -39,6 +39,9 @@ WORKLOADS = {
     # configs[0]: the reference's own CPU-runnable case (one window, 100 samples); for the GPU arm this is pure launch latency
     "v1_single_100": dict(model=1, n=1, ns=100, rate=200.0, flops_per_sample=5.8e3, bytes_per_window=8_024, single=True,
                           desc="configs[0]: single CPI v1 window, 100 IMU samples @ 200 Hz, fp64"),
+    # throughput regime of the headline kernel (not a BASELINE config): 125k windows = the per-GPU share of configs[3], in fp64
+    "v1_125k_200": dict(model=1, n=125_000, ns=200, rate=200.0, flops_per_sample=5.8e3, bytes_per_window=13_624,
+                        desc="125k-window batch x 200 samples, CPI v1, fp64 (large-batch regime of the configs[1] kernel)"),
     # configs[3] is quoted on 8 GPUs: 1M windows = 125k per GPU (weak-scaling unit); fp32-storage variant
     "v1_1m_200_fp32": dict(model=1, n=125_000, ns=200, rate=200.0, flops_per_sample=5.8e3, bytes_per_window=6_812, fp32=True,
                            desc="configs[3]: 1M-window batch x 200 samples, CPI v1, fp32 storage, 125k windows per GPU + NCCL all-gather"),
