@@ -44,7 +44,7 @@ __global__ void k_ffma(float* out, int iters, float a, float b) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-template <int W>  // W = 1: LDS.64, W = 2: LDS.128
+template <int W>  // W = 1: LDS.64, W = 2: LDS.128.  The address rotates with the iteration so that nothing can be hoisted.
 __global__ void k_lds(double* out, int iters) {
     extern __shared__ double sm[];
     const int n = blockDim.x * W * 8;
@@ -54,29 +54,60 @@ __global__ void k_lds(double* out, int iters) {
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int j = 0; j < 8; j++) {
+            const int row = (j + it) & 7;
             if (W == 1) {
-                s += sm[j * blockDim.x + threadIdx.x];
+                s += sm[row * blockDim.x + threadIdx.x];
             } else {
-                double2 v = reinterpret_cast<double2*>(sm)[j * blockDim.x + threadIdx.x];
+                double2 v = reinterpret_cast<double2*>(sm)[row * blockDim.x + threadIdx.x];
                 s += v.x + v.y;
             }
         }
-        if (s == 123.456) sm[threadIdx.x] = s;  // keep loads alive, never taken
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// SHFL.IDX of 32-bit values, 8 independent chains per thread, source lane = a per-lane table (like the trio gathers of the
+// tri-lane kernels: lane 3w+c reads 3w+(c+1)%3)
 __global__ void k_shfl(double* out, int iters) {
     int v[8];
+    const int lane = threadIdx.x & 31;
+    const int src = lane < 30 ? (lane / 3) * 3 + (lane % 3 + 1) % 3 : lane;
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = threadIdx.x + i;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = __shfl_xor_sync(0xffffffffu, v[i], 1 + (i & 3)) + 1;
+        for (int i = 0; i < 8; i++) v[i] = __shfl_sync(0xffffffffu, v[i], src) + 1;
     }
     int s = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) s += v[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// Mixed: per iteration NF dependent-free DFMA (8 chains) + NS double shuffles (2 SHFL each) + NL LDS.64 -- do the pipes overlap?
+template <int NF, int NS, int NL>
+__global__ void k_mix(double* out, int iters, double a, double b) {
+    extern __shared__ double sm[];
+    for (int i = threadIdx.x; i < blockDim.x * 8; i += blockDim.x) sm[i] = i * 1e-9;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int src = lane < 30 ? (lane / 3) * 3 + (lane % 3 + 1) % 3 : lane;
+    double x[8], y[4] = {1, 2, 3, 4}, l = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < (NF > NS ? (NF > NL ? NF : NL) : (NS > NL ? NS : NL)); r++) {
+            if (r < NF) x[r & 7] = fma(x[r & 7], a, b);
+            if (r < NS) y[r & 3] = __shfl_sync(0xffffffffu, y[r & 3], src);
+            if (r < NL) l += sm[((r + it) & 7) * blockDim.x + threadIdx.x];
+        }
+    }
+    double s = l;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += x[i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) s += y[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
@@ -88,6 +119,12 @@ __global__ void k_sincos(double* out, int iters, double x0) {
         acc += s * c;
         x += 1e-3;
     }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+__global__ void k_rcp(double* out, int iters, double x0) {
+    double x = x0 + threadIdx.x * 1e-4, acc = 0;
+    for (int it = 0; it < iters; it++) { acc += 1.0 / x; x += 1e-3; }
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
@@ -150,25 +187,36 @@ int main() {
         float ms = time_ms([&] { k_dfma<8><<<sms, thr>>>(out, iters, 1.0000001, 1e-9); });
         printf("{\"test\": \"dfma_threads_per_sm\", \"threads\": %d, \"ilp\": 8, \"tflops\": %.3f}\n", thr, 2.0 * 8 * iters * sms * thr / ms * 1e-9);
     }
-    // 4. LDS bandwidth per SM
-    for (int thr = 64; thr <= 512; thr *= 2) {
+    // 4. LDS bandwidth per SM (dynamic smem > 48 KB needs the opt-in attribute: the round-1 run died here)
+    CK(cudaFuncSetAttribute(k_lds<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_lds<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int thr = 64; thr <= 1024; thr *= 2) {
         const int iters = 20000;
         float ms1 = time_ms([&] { k_lds<1><<<sms, thr, thr * 8 * 8>>>(out, iters); });
         float ms2 = time_ms([&] { k_lds<2><<<sms, thr, thr * 16 * 8>>>(out, iters); });
         double b1 = 8.0 * 8 * iters * thr, b2 = 16.0 * 8 * iters * thr;  // bytes per SM
-        printf("{\"test\": \"lds\", \"threads\": %d, \"lds64_GBps_per_sm\": %.1f, \"lds128_GBps_per_sm\": %.1f}\n", thr, b1 / ms1 * 1e-6, b2 / ms2 * 1e-6);
+        printf("{\"test\": \"lds\", \"threads\": %d, \"lds64_GBps_per_sm\": %.1f, \"lds64_B_per_clk_per_sm\": %.1f, \"lds128_GBps_per_sm\": %.1f, \"lds128_B_per_clk_per_sm\": %.1f}\n",
+               thr, b1 / ms1 * 1e-6, b1 / ms1 * 1e-6 / (clk_khz * 1e-6), b2 / ms2 * 1e-6, b2 / ms2 * 1e-6 / (clk_khz * 1e-6));
     }
-    // 5. SHFL
+    // 5. SHFL.b32 throughput (a double costs two)
     for (int thr = 128; thr <= 1024; thr *= 2) {
         const int iters = 20000;
         float ms = time_ms([&] { k_shfl<<<sms, thr>>>(out, iters); });
-        printf("{\"test\": \"shfl\", \"threads\": %d, \"Gshfl_lanes_per_s_per_sm\": %.2f}\n", thr, 8.0 * iters * thr / ms * 1e-6);
+        double lanes = 8.0 * iters * thr;
+        printf("{\"test\": \"shfl_b32\", \"threads\": %d, \"Glanes_per_s_per_sm\": %.2f, \"lanes_per_clk_per_sm\": %.2f}\n", thr, lanes / ms * 1e-6, lanes / ms * 1e-6 / (clk_khz * 1e-6));
     }
-    // 6. sincos(double)
+    // 5b. pipe overlap at 512 threads/SM (4 warps per SMSP): time per iteration-warp in clocks for DFMA only, SHFL only, LDS only and mixes
+#define RUN_MIX(NF, NS, NL) { const int iters = 5000, thr = 512; \
+        float ms = time_ms([&] { k_mix<NF, NS, NL><<<sms, thr, thr * 64>>>(out, iters, 1.0000001, 1e-9); }); \
+        printf("{\"test\": \"mix\", \"threads\": %d, \"dfma\": %d, \"shfl_b32\": %d, \"lds64\": %d, \"clk_per_iter_per_sm\": %.1f}\n", thr, NF, NS, NL, ms * 1e-3 * clk_khz * 1e3 / iters); }
+    RUN_MIX(32, 0, 0) RUN_MIX(0, 16, 0) RUN_MIX(0, 0, 16) RUN_MIX(32, 16, 0) RUN_MIX(32, 0, 16) RUN_MIX(0, 16, 16) RUN_MIX(32, 16, 16) RUN_MIX(32, 8, 8) RUN_MIX(32, 32, 0)
+    // 6. sincos(double), 1/x (double)
     for (int thr = 128; thr <= 1024; thr *= 4) {
         const int iters = 4000;
         float ms = time_ms([&] { k_sincos<<<sms, thr>>>(out, iters, 0.01); });
-        printf("{\"test\": \"sincos_f64\", \"threads\": %d, \"ns_per_warp_call\": %.2f, \"Gcalls_per_s\": %.3f}\n", thr, ms * 1e6 / iters / (thr / 32), (double)iters * thr * sms / ms * 1e-6);
+        printf("{\"test\": \"sincos_f64\", \"threads\": %d, \"clk_per_warp_call_per_smsp\": %.1f, \"Gcalls_per_s\": %.3f}\n", thr, ms * 1e-3 * clk_khz * 1e3 / iters / (thr / 128.0), (double)iters * thr * sms / ms * 1e-6);
+        float ms2 = time_ms([&] { k_rcp<<<sms, thr>>>(out, iters, 0.01); });
+        printf("{\"test\": \"rcp_f64\", \"threads\": %d, \"clk_per_warp_call_per_smsp\": %.1f}\n", thr, ms2 * 1e-3 * clk_khz * 1e3 / iters / (thr / 128.0));
     }
     return 0;
 }
