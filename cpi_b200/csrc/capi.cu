@@ -175,7 +175,7 @@ int cpi_preintegrate_batch_host(int model, int dtype, int64_t n_windows, const i
     int nchunk = 1;
     if (in_bytes >= ((size_t)24 << 20) && n_windows >= 8 * (int64_t)d.sms) nchunk = Scratch::NSTREAM;
     if (const char* e = getenv("CPI_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= Scratch::NSTREAM) nchunk = v; }   // A/B measurements
-    const int cap = (model == 1 && !avg) ? cpi::preint_ws_cap(dtype) : cpi::preint_pick_wpb(model, dtype, (int64_t)1 << 40, d.sms);
+    const int cap = cpi::preint_cap(model, dtype, flags, d.sms);     // windows per CTA of the kernel preint_launch will select
     int64_t need = (n_windows + d.sms - 1) / d.sms;
     const int wpb = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
     const int64_t blocks = (n_windows + wpb - 1) / wpb;

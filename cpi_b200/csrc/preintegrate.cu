@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include "cpi_common.cuh"
 #include "cpi_kernels.h"
+#include "tma.cuh"
 
 namespace cpi {
 
@@ -75,24 +76,6 @@ static_assert(tile_bytes<1, double>() <= 232448 && tile_bytes<2, double>() <= 23
 static_assert(tile_off_T<1, float>() % 16 == 0 && tile_off_T<2, float>() % 16 == 0 && tile_off_buf<1, float>() % 16 == 0 &&
               tile_off_buf<2, float>() % 16 == 0 && tile_off_buf<1, double>() % 16 == 0 && tile_off_buf<2, double>() % 16 == 0,
               "cp.async.bulk destinations must be 16-byte aligned");
-
-// ---- TMA (1-D bulk copy) + mbarrier primitives: SASS UBLKCP / SYNCS ---------------------------------------------------
-CPI_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-CPI_DEV void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
-CPI_DEV void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-CPI_DEV void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-CPI_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
-}
-CPI_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- block loaders ----------------------------------------------------------------------------------------------------
 #define SM(buf, idx) (buf)[(idx) * S]
@@ -1096,7 +1079,6 @@ template <class T> struct TileWS {
 static_assert(TileWS<double>::bytes <= 232448 && TileWS<float>::bytes <= 232448, "ws tile exceeds 227 KB");
 static_assert(TileWS<double>::off_buf % 16 == 0 && TileWS<float>::off_buf % 16 == 0 && TileWS<double>::off_pair % 8 == 0, "alignment");
 
-CPI_DEV void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
 template <class T>
 __global__ void __launch_bounds__(256, 1) k_preintegrate_ws(const PreintParams p) {
@@ -1299,6 +1281,14 @@ int preint_pick_wpb(int model, int dtype, int64_t n_windows, int num_sms) {
 
 int preint_ws_cap(int dtype) { return dtype == 32 ? TileWS<float>::S : TileWS<double>::S; }
 
+static bool use_legacy() { static const bool v = getenv("CPI_B200_LEGACY") != nullptr || getenv("CPI_B200_FUSED") != nullptr; return v; }
+
+int preint_cap(int model, int dtype, int flags, int num_sms) {
+    if (!use_legacy() && preint_tri_supported(model, flags)) return preint_tri_cap();
+    if (model == 1 && !(flags & CPI_FLAG_IMU_AVG) && getenv("CPI_B200_FUSED") == nullptr) return preint_ws_cap(dtype);
+    return preint_pick_wpb(model, dtype, (int64_t)1 << 40, num_sms);
+}
+
 template <class T>
 static cudaError_t launch_typed(int model, int flags, const PreintParams& p, int grid, int block, cudaStream_t st) {
     const bool avg = flags & CPI_FLAG_IMU_AVG, ana = flags & CPI_FLAG_ANALYTIC_JACOBIANS;
@@ -1312,6 +1302,12 @@ cudaError_t preint_launch(int model, int dtype, int flags, const PreintParams& p
     if (p.n_windows == 0) return cudaSuccess;
     if (max_smem_bytes < 232448) return cudaErrorInvalidConfiguration;
     static const bool force_fused = getenv("CPI_B200_FUSED") != nullptr;
+    // default for the non-imu_avg model-1 path: the tri-lane register-tile kernel (preintegrate_tri.cu).  CPI_B200_LEGACY=1
+    // selects the round-1 lane-per-window kernels (A/B measurements only).
+    if (!use_legacy() && preint_tri_supported(model, flags) && p.n_windows < (int64_t)2147483647) {
+        if (launches) *launches = 1;
+        return preint_launch_tri(model, dtype, p, num_sms, st);
+    }
     // fp32 tiles are small enough that the fused kernel holds 128 windows (4 full warps) per SM: for batches beyond one wave
     // of the warp-specialised kernel it is the faster one (measured: 14.2 vs 13.1 M windows/s on 125k x 200)
     const bool ws_pays = dtype != 32 || p.n_windows <= (int64_t)num_sms * TileWS<float>::S;

@@ -1,0 +1,671 @@
+// K1 / K2, "tri-lane" mapping: THREE LANES PER WINDOW, ten windows per warp, the per-window state distributed over the
+// three lanes' REGISTERS and exchanged with warp shuffles.  CpiV1::feed_IMU (cpi/CpiV1.h:62-361) and CpiV2::feed_IMU
+// (cpi/CpiV2.h:84-467, state_transition_jacobians = true) of rpng/cpi.  Default kernels for the non-imu_avg modes; the
+// lane-per-window kernels of preintegrate.cu serve imu_avg and model 2's analytic-Jacobian mode.
+//
+// Why three: every quantity on the path is a 3-vector or a 3x3 block, and every equation is equivariant under a CYCLIC
+// relabelling of the three axes (a proper rotation: cross products keep their form).  Lane c of a window works in the
+// frame whose axes are (c, c+1, c+2) and owns COLUMN 0 of every 3x3 block IN ITS OWN FRAME -- i.e. original column c,
+// stored in the order (c, c+1, c+2).  All three lanes therefore execute the same instructions on "column 0", register
+// indices are static everywhere, and fetching a neighbour's column is two or three SHFLs with a fixed index permutation
+// (gather_cols).  Window-uniform inputs (w_hat, a_hat, the rotations) are simply read / gathered in rotated order.
+//
+// Covariance blocks are stored in the orientation that makes the Lyapunov right-hand side column-local
+// (P_dot = F P + P F^T; column c of F_IK P_KJ needs only column c of P_KJ, column c of P_IK F_JK^T needs all of P_IK
+// unless F_JK is the identity):
+//     TG = P_theta,bg   TT = P_theta,theta   GV = P_bg,v   TV = P_theta,v   AV = P_ba,v   VV = P_v,v
+//     TP = P_theta,p    GP = P_bg,p          AP = P_ba,p   VP = P_v,p       PP = P_p,p
+// With this choice only FOUR quantities per RK4 stage cross lanes: the full TG and TT stage values (needed by GV, TV)
+// and one row of the symmetric VV / PP right-hand sides: 13 doubles per stage per lane instead of the 943 shared-memory
+// operations per sample of the lane-per-window layout, and the covariance tile no longer lives in shared memory at
+// all (residency is register-bound, not smem-bound).  The four RK4 stages are the reference's (CpiV1.h:272-353).
+//
+// Measured on B200 (profiles/microbench_r02.jsonl): SHFL.b32 = 1 warp-instr/clk/SM, LDS.64 = 1 warp-instr/clk/SM on the
+// same MIO pipe, DFMA = 2 warp-instr/clk/SM, and SHFL overlaps fully with DFMA.
+#include <cstdlib>
+#include "cpi_common.cuh"
+#include "cpi_kernels.h"
+#include "tma.cuh"
+
+namespace cpi {
+
+constexpr int TRI_WPW = 10;                 // windows per warp (lanes 30, 31 idle)
+constexpr int TRI_THREADS = 256;            // CTA size (compile-time: slot stride)
+constexpr int TRI_WPB = TRI_WPW * TRI_THREADS / 32;   // window slots per CTA
+constexpr int TRI_BUF_STRIDE = 272;         // bytes of sample staging per window: 2 x 128 B + 16 B pad (bank spread; 16-B aligned for TMA)
+
+template <class T> CPI_DEV T shf(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// columns 1 and 2 (own frame) of a block whose column 0 each lane of the trio holds:  X1[k] = next.V[(k+2)%3], X2[k] = prev.V[(k+1)%3]
+template <class T> CPI_DEV void gather_cols(const T* V, int nx, int pv, T* X1, T* X2) {
+    X1[0] = shf(V[2], nx); X1[1] = shf(V[0], nx); X1[2] = shf(V[1], nx);
+    X2[0] = shf(V[1], pv); X2[1] = shf(V[2], pv); X2[2] = shf(V[0], pv);
+}
+
+// ---- per-model layout --------------------------------------------------------------------------------------------------
+// RK4 stage values handed from the (theta|v)-column group to the p-column group through LANE-PRIVATE shared memory
+// slots, [entry][thread]: TV, GV, AV, VV (model 2: + CV) for the four stages.
+template <int MODEL> struct TriL {
+    static constexpr int NSL = (MODEL == 1 ? 12 : 15) * 4;
+    // front state parked in lane-private smem during the covariance step: bw, ba, alpha, beta, then
+    //   model 1: J_q, J_a, J_b, H_a, H_b (own columns)      model 2: g_k and the own columns of the 7 non-trivial Discrete_J_b blocks
+    static constexpr int NFS = (MODEL == 1) ? 23 : 32;
+};
+enum : int { FS_BW = 0, FS_BA = 3, FS_AL = 6, FS_BE = 7, FS_JQ = 8, FS_JA = 11, FS_JB = 14, FS_HA = 17, FS_HB = 20,
+             FS_GK = 8, FS_DTG = 11, FS_DVG = 14, FS_DPG = 17, FS_DVA = 20, FS_DPA = 23, FS_DVL = 26, FS_DPL = 29 };
+template <int MODEL, class T> struct TriSmem {
+    static constexpr size_t off_fs = (size_t)TriL<MODEL>::NSL * TRI_THREADS * sizeof(T);
+    static constexpr size_t off_buf = off_fs + (size_t)TriL<MODEL>::NFS * TRI_THREADS * 8;
+    static constexpr size_t off_bar = off_buf + (size_t)TRI_WPB * TRI_BUF_STRIDE;
+    static constexpr size_t bytes = off_bar + (size_t)TRI_WPB * 16;
+};
+
+#define SLT(e) sl[(e) * TRI_THREADS]
+#define FST(e) fs[(e) * TRI_THREADS]
+#define CN(s) ((s) < 2 ? hdt : dt)                       /* x_{s+2} = x_1 + CN(s) k_{s+1}:  dt/2, dt/2, dt   (CpiV1.h:312, 323, 344) */
+#define KSUM(ks, k, s) ((s) == 0 ? (k) : ((s) == 3 ? (ks) + (k) : fma(T(2), (k), (ks))))   /* ((k1 + 2 k2) + 2 k3) + k4  (CpiV1.h:352) */
+#define CPI_FENCE() asm volatile("" ::: "memory")
+
+// -(R^T u): element i = -(column i of R) . u      (R row-major 3x3)
+template <class T> CPI_DEV void negRt(const T* R, const T* u, T* o) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) o[i] = -(R[i] * u[0] + R[3 + i] * u[1] + R[6 + i] * u[2]);
+}
+
+// Covariance state of one lane (column 0 of each block in the lane's frame)
+template <class T> struct TriP {
+    T TG[3], TT[3], GV[3], TV[3], AV[3], VV[3], TP[3], GP[3], AP[3], VP[3], PP[3];
+};
+
+// One RK4 step of the covariance (model 1: CpiV1.h:272-353).  w, ah: estimated readings; R, Rm, R1: old / mid / new
+// rotation (row-major, lane frame); pgg, paa: the scalar diagonal blocks P_bg,bg and P_ba,ba at the start of the step.
+template <int MODEL, class T>
+CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, const T* w, const T* ah, const T* gt, const T* R, const T* Rm, const T* R1, T pgg, T paa, T dt, T dt6,
+                          T q_w, T q_wb, T q_a, T q_ab, int nx, int pv) {
+    const T hdt = dt * T(0.5);
+    constexpr int NS = (MODEL == 1) ? 12 : 15;            // slot entries per stage
+    // Model 2 (CpiV2.h:326-443): the clone rows c of P_big are re-initialised from the theta rows at every step (B_k), so within a
+    // step  P_cg = TG(start), P_cc = TT(start), P_ca = 0  are constant and only three transient blocks evolve:
+    //     TC = P_theta,c  (starts as TT):  TC' = -W TC - TG(start)^T            [needs nothing cross-lane; TV and CV need all of it]
+    //     CV = P_c,v      (starts as TV):  CV' = TC^T A_s^T + TT(start) C_s^T
+    //     CP = P_c,p      (starts as TP):  CP' = CV                            [recomputed from CV's stage values]
+    // and the v rows gain  C_s P_c,J  with  C_s = -R_s^T [g_tau x]  (CpiV2.h:335).
+    {   // ---- group 1a: TG, TT, GV, TV, stage by stage (self-contained: needs only w, the rotations and a_hat)
+        T xTG[3], xTT[3], xGV[3], xTV[3], xTC[3], xCV[3];
+        T sTG[3], sTT[3], sGV[3], sTV[3];
+        T G1s[3], G2s[3], tts[3];                             // model 2: TG(start) columns 1, 2 and TT(start) entries 11, 21, 22
+#pragma unroll
+        for (int e = 0; e < 3; e++) { xTG[e] = P.TG[e]; xTT[e] = P.TT[e]; xGV[e] = P.GV[e]; xTV[e] = P.TV[e]; xTC[e] = P.TT[e]; xCV[e] = P.TV[e]; }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const T* Rs = (s == 0) ? R : (s == 3 ? R1 : Rm);
+            const T rc[3] = {Rs[0], Rs[3], Rs[6]};            // column 0 of R_s
+            T a0[3];
+            cross(ah, rc, a0);                                // row 0 of A_s = -R_s^T [a x]  (row i = a x r_i)
+            // cross-lane: full TG_s, the three missing entries of the symmetric TT_s
+            T TG1[3], TG2[3];
+            gather_cols(xTG, nx, pv, TG1, TG2);
+            const T t11 = shf(xTT[0], nx), t21 = shf(xTT[1], nx), t22 = shf(xTT[0], pv);
+            // stage values the later groups need
+#pragma unroll
+            for (int e = 0; e < 3; e++) { SLT(s * NS + e) = xTV[e]; SLT(s * NS + 3 + e) = xGV[e]; if (MODEL == 2) SLT(s * NS + 12 + e) = xCV[e]; }
+            const T pg_s = (s == 0) ? pgg : fma(q_wb, (s == 3 ? dt : hdt), pgg);
+            T kTG[3], kTT[3], kGV[3], kTV[3];
+            T c0[3], TC1[3], TC2[3];
+            if (MODEL == 2) {
+                cross(gt, rc, c0);                            // row 0 of C_s = -R_s^T [g_tau x]
+                if (s == 0) {
+#pragma unroll
+                    for (int e = 0; e < 3; e++) { G1s[e] = TG1[e]; G2s[e] = TG2[e]; }
+                    tts[0] = t11; tts[1] = t21; tts[2] = t22;
+                    TC1[0] = xTT[1]; TC1[1] = t11; TC1[2] = t21; TC2[0] = xTT[2]; TC2[1] = t21; TC2[2] = t22;   // TC(start) = TT(start), symmetric
+                } else gather_cols(xTC, nx, pv, TC1, TC2);
+            }
+            // TG:  -W x - pgg_s I
+            cross(xTG, w, kTG);
+            kTG[0] -= pg_s;
+            // TT:  N + N^T + q_w I,  N = -W TT - TG^T  ->  N[:,0] = TT_0 x w - row0(TG),  N[0,j] = (TT_j x w)[0] - TG[j,0]
+            {
+                T n0[3];
+                cross(xTT, w, n0);
+                n0[0] -= xTG[0]; n0[1] -= TG1[0]; n0[2] -= TG2[0];
+                const T n01 = (t11 * w[2] - t21 * w[1]) - xTG[1];     // TT_1 = (TT01, TT11, TT21)
+                const T n02 = (t21 * w[2] - t22 * w[1]) - xTG[2];     // TT_2 = (TT02, TT12, TT22)
+                kTT[0] = n0[0] + n0[0] + q_w; kTT[1] = n0[1] + n01; kTT[2] = n0[2] + n02;
+            }
+            // GV:  TG^T A_s[0,:]^T  -> element i = (column i of TG) . a0
+            kGV[0] = xTG[0] * a0[0] + xTG[1] * a0[1] + xTG[2] * a0[2];
+            kGV[1] = TG1[0] * a0[0] + TG1[1] * a0[1] + TG1[2] * a0[2];
+            kGV[2] = TG2[0] * a0[0] + TG2[1] * a0[1] + TG2[2] * a0[2];
+            // TV:  -W TV - GV + TT A_s[0,:]^T
+            cross(xTV, w, kTV);
+            kTV[0] = (kTV[0] - xGV[0]) + (xTT[0] * a0[0] + xTT[1] * a0[1] + xTT[2] * a0[2]);
+            kTV[1] = (kTV[1] - xGV[1]) + (xTT[1] * a0[0] + t11 * a0[1] + t21 * a0[2]);
+            kTV[2] = (kTV[2] - xGV[2]) + (xTT[2] * a0[0] + t21 * a0[1] + t22 * a0[2]);
+            T kTC[3], kCV[3];
+            if (MODEL == 2) {
+                // GV += TG(start)^T C_s[0,:]^T ;  TV += TC C_s[0,:]^T
+                kGV[0] += P.TG[0] * c0[0] + P.TG[1] * c0[1] + P.TG[2] * c0[2];
+                kGV[1] += G1s[0] * c0[0] + G1s[1] * c0[1] + G1s[2] * c0[2];
+                kGV[2] += G2s[0] * c0[0] + G2s[1] * c0[1] + G2s[2] * c0[2];
+#pragma unroll
+                for (int e = 0; e < 3; e++) kTV[e] += xTC[e] * c0[0] + TC1[e] * c0[1] + TC2[e] * c0[2];
+                // TC:  -W TC - TG(start)^T  (column 0: minus row 0 of TG(start))
+                cross(xTC, w, kTC);
+                kTC[0] -= P.TG[0]; kTC[1] -= G1s[0]; kTC[2] -= G2s[0];
+                // CV:  TC^T A_s[0,:]^T + TT(start) C_s[0,:]^T
+                kCV[0] = (xTC[0] * a0[0] + xTC[1] * a0[1] + xTC[2] * a0[2]) + (P.TT[0] * c0[0] + P.TT[1] * c0[1] + P.TT[2] * c0[2]);
+                kCV[1] = (TC1[0] * a0[0] + TC1[1] * a0[1] + TC1[2] * a0[2]) + (P.TT[1] * c0[0] + tts[0] * c0[1] + tts[1] * c0[2]);
+                kCV[2] = (TC2[0] * a0[0] + TC2[1] * a0[1] + TC2[2] * a0[2]) + (P.TT[2] * c0[0] + tts[1] * c0[1] + tts[2] * c0[2]);
+            }
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                sTG[e] = KSUM(sTG[e], kTG[e], s); sTT[e] = KSUM(sTT[e], kTT[e], s); sGV[e] = KSUM(sGV[e], kGV[e], s); sTV[e] = KSUM(sTV[e], kTV[e], s);
+                if (s < 3) {
+                    xTG[e] = fma(kTG[e], CN(s), P.TG[e]); xTT[e] = fma(kTT[e], CN(s), P.TT[e]); xGV[e] = fma(kGV[e], CN(s), P.GV[e]);
+                    xTV[e] = fma(kTV[e], CN(s), P.TV[e]);
+                    if (MODEL == 2) { xTC[e] = fma(kTC[e], CN(s), P.TT[e]); xCV[e] = fma(kCV[e], CN(s), P.TV[e]); }
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            P.TG[e] = fma(dt6, sTG[e], P.TG[e]); P.TT[e] = fma(dt6, sTT[e], P.TT[e]); P.GV[e] = fma(dt6, sGV[e], P.GV[e]);
+            P.TV[e] = fma(dt6, sTV[e], P.TV[e]);
+        }
+    }
+    CPI_FENCE();
+    {   // ---- group 1b: AV, VV (need TV's stage values)
+        T xAV[3], xVV[3], sAV[3], sVV[3];
+#pragma unroll
+        for (int e = 0; e < 3; e++) { xAV[e] = P.AV[e]; xVV[e] = P.VV[e]; }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const T* Rs = (s == 0) ? R : (s == 3 ? R1 : Rm);
+            const T rc[3] = {Rs[0], Rs[3], Rs[6]};
+            T tv[3];
+#pragma unroll
+            for (int e = 0; e < 3; e++) { tv[e] = SLT(s * NS + e); SLT(s * NS + 6 + e) = xAV[e]; SLT(s * NS + 9 + e) = xVV[e]; }
+            const T pa_s = (s == 0) ? paa : fma(q_ab, (s == 3 ? dt : hdt), paa);
+            T kAV[3], kVV[3];
+            // AV:  paa_s B_s[0,:]^T = -paa_s (column 0 of R_s)
+#pragma unroll
+            for (int e = 0; e < 3; e++) kAV[e] = -(pa_s * rc[e]);
+            // VV:  M + M^T + q_a I,  M[:,0] = A_s TV_0 + B_s AV_0 = -R_s^T (a x TV_0 + AV_0)
+            {
+                T u[3], m0[3];
+                cross(ah, tv, u);
+#pragma unroll
+                for (int e = 0; e < 3; e++) u[e] += xAV[e];
+                if (MODEL == 2) {                             // + C_s CV_0 = -R_s^T (g_tau x CV_0)
+                    T cv[3], u2[3];
+#pragma unroll
+                    for (int e = 0; e < 3; e++) cv[e] = SLT(s * NS + 12 + e);
+                    cross(gt, cv, u2);
+#pragma unroll
+                    for (int e = 0; e < 3; e++) u[e] += u2[e];
+                }
+                negRt(Rs, u, m0);
+                const T m01 = shf(m0[2], nx), m02 = shf(m0[1], pv);   // M[0,1], M[0,2]
+                kVV[0] = m0[0] + m0[0] + q_a; kVV[1] = m0[1] + m01; kVV[2] = m0[2] + m02;
+            }
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                sAV[e] = KSUM(sAV[e], kAV[e], s); sVV[e] = KSUM(sVV[e], kVV[e], s);
+                if (s < 3) { xAV[e] = fma(kAV[e], CN(s), P.AV[e]); xVV[e] = fma(kVV[e], CN(s), P.VV[e]); }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 3; e++) { P.AV[e] = fma(dt6, sAV[e], P.AV[e]); P.VV[e] = fma(dt6, sVV[e], P.VV[e]); }
+    }
+    CPI_FENCE();
+    {   // ---- group 2: the p-column blocks TP, GP, AP, VP, PP
+        T xTP[3], xGP[3], xAP[3], xVP[3], xPP[3];
+        T sTP[3], sGP[3], sAP[3], sVP[3], sPP[3];
+#pragma unroll
+        for (int e = 0; e < 3; e++) { xTP[e] = P.TP[e]; xGP[e] = P.GP[e]; xAP[e] = P.AP[e]; xVP[e] = P.VP[e]; xPP[e] = P.PP[e]; }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const T* Rs = (s == 0) ? R : (s == 3 ? R1 : Rm);
+            T tv[3], gv[3], av[3], vv[3];
+#pragma unroll
+            for (int e = 0; e < 3; e++) { tv[e] = SLT(s * NS + e); gv[e] = SLT(s * NS + 3 + e); av[e] = SLT(s * NS + 6 + e); vv[e] = SLT(s * NS + 9 + e); }
+            T kTP[3], kVP[3], kPP[3];
+            // TP:  -W TP - GP + TV
+            cross(xTP, w, kTP);
+#pragma unroll
+            for (int e = 0; e < 3; e++) kTP[e] = (kTP[e] - xGP[e]) + tv[e];
+            // VP:  A_s TP_0 + B_s AP_0 + VV_0
+            {
+                T u[3], m0[3];
+                cross(ah, xTP, u);
+#pragma unroll
+                for (int e = 0; e < 3; e++) u[e] += xAP[e];
+                if (MODEL == 2) {                             // + C_s CP_0,  CP_s = TP(start) + CN(s-1) CV_{s-1}
+                    T cp[3], u2[3];
+#pragma unroll
+                    for (int e = 0; e < 3; e++) cp[e] = (s == 0) ? P.TP[e] : fma((T)SLT((s - 1) * NS + 12 + e), CN(s - 1), P.TP[e]);
+                    cross(gt, cp, u2);
+#pragma unroll
+                    for (int e = 0; e < 3; e++) u[e] += u2[e];
+                }
+                negRt(Rs, u, m0);
+#pragma unroll
+                for (int e = 0; e < 3; e++) kVP[e] = m0[e] + vv[e];
+            }
+            // PP:  VP + VP^T
+            kPP[0] = xVP[0] + xVP[0]; kPP[1] = xVP[1] + shf(xVP[2], nx); kPP[2] = xVP[2] + shf(xVP[1], pv);
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                sTP[e] = KSUM(sTP[e], kTP[e], s); sGP[e] = KSUM(sGP[e], gv[e], s); sAP[e] = KSUM(sAP[e], av[e], s);
+                sVP[e] = KSUM(sVP[e], kVP[e], s); sPP[e] = KSUM(sPP[e], kPP[e], s);
+                if (s < 3) {
+                    xTP[e] = fma(kTP[e], CN(s), P.TP[e]); xGP[e] = fma(gv[e], CN(s), P.GP[e]); xAP[e] = fma(av[e], CN(s), P.AP[e]);
+                    xVP[e] = fma(kVP[e], CN(s), P.VP[e]);
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            P.TP[e] = fma(dt6, sTP[e], P.TP[e]); P.GP[e] = fma(dt6, sGP[e], P.GP[e]); P.AP[e] = fma(dt6, sAP[e], P.AP[e]);
+            P.VP[e] = fma(dt6, sVP[e], P.VP[e]); P.PP[e] = fma(dt6, sPP[e], P.PP[e]);
+        }
+    }
+    CPI_FENCE();
+}
+
+// D v  with  D = I - a [w x] + b [w x]^2 :   v - a (w x v) + b (w x (w x v));  second result with (a2, b2) on the same cross products
+CPI_DEV void rot_col2(double a, double b, double a2, double b2, const double* w, const double* v, double* o, double* o2) {
+    double t[3], u[3];
+    cross(w, v, t);
+    cross(w, t, u);
+#pragma unroll
+    for (int e = 0; e < 3; e++) { o[e] = (v[e] - a * t[e]) + b * u[e]; o2[e] = (v[e] - a2 * t[e]) + b2 * u[e]; }
+}
+CPI_DEV void rot_col(double a, double b, const double* w, const double* v, double* o) {
+    double t[3], u[3];
+    cross(w, v, t);
+    cross(w, t, u);
+#pragma unroll
+    for (int e = 0; e < 3; e++) o[e] = (v[e] - a * t[e]) + b * u[e];
+}
+
+template <int MODEL, class T>
+__global__ void __launch_bounds__(TRI_THREADS, 1) k_preintegrate_tri(const PreintParams p) {
+    using SM_ = TriSmem<MODEL, T>;
+    constexpr int CH = 8 / (int)sizeof(T) * 2;            // samples per TMA chunk: 2 (fp64) or 4 (fp32) = 112 B in one aligned 128-B fetch
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool lane_ok = lane < 3 * TRI_WPW;
+    const int trio = lane_ok ? lane / 3 : 0;
+    const int c = lane_ok ? lane - 3 * trio : 0;          // axis offset of this lane's frame
+    const int i0 = c, i1 = (c + 1) % 3, i2 = (c + 2) % 3; // original index of frame axis 0, 1, 2
+    const int nx = lane_ok ? 3 * trio + i1 : lane, pv = lane_ok ? 3 * trio + i2 : lane;
+    const int wslot = wid * TRI_WPW + trio;
+    const int64_t win = (int64_t)blockIdx.x * p.wpb + wslot;
+    const bool active = lane_ok && wslot < p.wpb && win < p.n_windows;
+    if (wid * TRI_WPW >= p.wpb || (int64_t)blockIdx.x * p.wpb + wid * TRI_WPW >= p.n_windows) return;   // whole warp idle (warp-uniform)
+
+    T* sl = reinterpret_cast<T*>(smem_raw) + threadIdx.x;
+    double* fs = reinterpret_cast<double*>(smem_raw + SM_::off_fs) + threadIdx.x;
+    const T* buf = reinterpret_cast<const T*>(smem_raw + SM_::off_buf + (size_t)wslot * TRI_BUF_STRIDE);
+    const uint32_t buf0 = smem_u32(buf);
+    const uint32_t bar0 = smem_u32(smem_raw + SM_::off_bar + (size_t)wslot * 16);
+
+    // ---- per-window constants (setLinearizationPoints, CpiBase.h:73-80), in the lane frame
+    int64_t o0 = 0, nsteps = 0;
+#pragma unroll
+    for (int e = 0; e < TriL<MODEL>::NFS; e++) FST(e) = 0.0;
+    if (active) {
+        const T* lin = reinterpret_cast<const T*>(p.lin) + win * CPI_LIN_DOUBLES;
+        FST(FS_BW) = (double)lin[i0]; FST(FS_BW + 1) = (double)lin[i1]; FST(FS_BW + 2) = (double)lin[i2];
+        FST(FS_BA) = (double)lin[3 + i0]; FST(FS_BA + 1) = (double)lin[3 + i1]; FST(FS_BA + 2) = (double)lin[3 + i2];
+        if (MODEL == 2) {                                            // g_k = quat_2_Rot(q_k_lin) * grav  (CpiV2.h:99, 202, 315), rotated into the lane frame
+            const double q[4] = {(double)lin[6], (double)lin[7], (double)lin[8], (double)lin[9]}, g[3] = {(double)lin[10], (double)lin[11], (double)lin[12]};
+            double RG[9], gk[3];
+            quat_2_Rot(q, RG);
+            mv33(RG, g, gk);
+            FST(FS_GK) = c == 0 ? gk[0] : (c == 1 ? gk[1] : gk[2]);
+            FST(FS_GK + 1) = c == 0 ? gk[1] : (c == 1 ? gk[2] : gk[0]);
+            FST(FS_GK + 2) = c == 0 ? gk[2] : (c == 1 ? gk[0] : gk[1]);
+        }
+        if (p.offsets) { o0 = p.offsets[win]; nsteps = p.offsets[win + 1] - o0; }
+        else { o0 = win * p.ns_uniform; nsteps = p.ns_uniform; }
+        if (nsteps < 0) nsteps = 0;
+    }
+    const T* sp = reinterpret_cast<const T*>(p.samples) + o0 * CPI_SAMPLE_DOUBLES;
+    const int wmax = __reduce_max_sync(0xffffffffu, (int)nsteps);
+
+    // ---- TMA pipeline: lane 0 of the trio stages the window's stream, two 128-byte chunks in flight
+    const int shift = (int)(((uintptr_t)sp & 15) / sizeof(T));      // misalignment of the window start w.r.t. 16 bytes, in elements
+    const int64_t n_tma = nsteps > 0 ? (nsteps - 1) / CH : 0;       // chunks with at least one more sample after them
+    if (active && c == 0) {
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            if (k < n_tma) {
+                mbar_arrive_expect_tx(bar0 + 8 * k, 128);
+                bulk_g2s(buf0 + 128 * k, sp + 7 * CH * k - shift, 128, bar0 + 8 * k);
+            }
+    }
+    __syncwarp();                                                    // barrier init visible to the trio before anyone polls
+
+    // ---- state (CpiBase.h:99-124 initialisers), lane frame
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};                       // full old rotation, row-major
+    double DT = 0.0, pgg = 0.0, paa = 0.0;
+    TriP<T> P;
+#pragma unroll
+    for (int e = 0; e < 3; e++) P.TG[e] = P.TT[e] = P.GV[e] = P.TV[e] = P.AV[e] = P.VV[e] = P.TP[e] = P.GP[e] = P.AP[e] = P.VP[e] = P.PP[e] = T(0);
+
+#pragma unroll 1
+    for (int it = 0; it < wmax; it++) {
+        // ---- fetch entry `it` in the lane frame; finished windows run a NULL step (dt = 0: an exact no-op, see below)
+        double wm[3] = {0, 0, 0}, am[3] = {0, 0, 0}, dt = 0.0;
+        if (it < nsteps) {
+            if (it < CH * n_tma) {
+                const int64_t ck = it / CH;
+                const int b = (int)(ck & 1), j = (int)(it % CH);
+                if (j == 0) {
+                    mbar_wait(bar0 + 8 * b, (uint32_t)((ck >> 1) & 1));
+                    // the other buffer (chunk ck-1) has been consumed by all three lanes: refill it with chunk ck+1
+                    if (c == 0 && ck >= 1 && ck + 1 < n_tma) {
+                        fence_proxy_async();
+                        mbar_arrive_expect_tx(bar0 + 8 * (b ^ 1), 128);
+                        bulk_g2s(buf0 + 128 * (b ^ 1), sp + 7 * CH * (ck + 1) - shift, 128, bar0 + 8 * (b ^ 1));
+                    }
+                }
+                const T* src = buf + b * (128 / (int)sizeof(T)) + shift + 7 * j;
+                wm[0] = (double)src[i0]; wm[1] = (double)src[i1]; wm[2] = (double)src[i2];
+                am[0] = (double)src[3 + i0]; am[1] = (double)src[3 + i1]; am[2] = (double)src[3 + i2];
+                dt = (double)src[6];
+            } else {
+                const T* src = sp + (int64_t)it * CPI_SAMPLE_DOUBLES;
+                wm[0] = (double)__ldg(src + i0); wm[1] = (double)__ldg(src + i1); wm[2] = (double)__ldg(src + i2);
+                am[0] = (double)__ldg(src + 3 + i0); am[1] = (double)__ldg(src + 3 + i1); am[2] = (double)__ldg(src + 3 + i2);
+                dt = (double)__ldg(src + 6);
+            }
+        }
+        DT += dt;                                                    // CpiV1.h:69 (before the dt == 0 return)
+
+        // ---- estimated readings (CpiV1.h:77-86)
+        const double wh[3] = {wm[0] - FST(FS_BW), wm[1] - FST(FS_BW + 1), wm[2] - FST(FS_BW + 2)};
+        double ah[3] = {am[0] - FST(FS_BA), am[1] - FST(FS_BA + 1), am[2] - FST(FS_BA + 2)};
+        double g_tau[3] = {0.0, 0.0, 0.0};
+        if (MODEL == 2) {                                            // a_hat = a_m - b_a - R_k2tau R_G2k g  with the OLD rotation (CpiV2.h:99)
+            const double gk[3] = {FST(FS_GK), FST(FS_GK + 1), FST(FS_GK + 2)};
+            mv33(R, gk, g_tau);
+            ah[0] -= g_tau[0]; ah[1] -= g_tau[1]; ah[2] -= g_tau[2];
+        }
+        const double mag2 = wh[0] * wh[0] + wh[1] * wh[1] + wh[2] * wh[2];
+        const double mag = sqrt(mag2);
+        const double th = mag * dt;
+        // CpiV1.h:101.  dt == 0 is the reference's silent no-op (CpiV1.h:72-74); the Taylor branch at dt = 0 gives exactly that
+        // (D = I, every coefficient 0), so null steps need no branch around the shuffles below.
+        const bool small_w = mag < 0.008726646 || dt == 0.0;
+        double sn, cs_, sh, ch;
+        sincos(th, &sn, &cs_);
+        sincos(mag * 0.5 * dt, &sh, &ch);
+        const double im = small_w ? 0.0 : 1.0 / mag;
+        const double im2 = im * im;
+
+        // ---- relative rotation: own column of the new and the mid-point rotation (CpiV1.h:119-124, 267-269), then the full matrices
+        const double a1 = small_w ? dt : sn * im, b1 = small_w ? (dt * dt) * 0.5 : (1.0 - cs_) * im2;
+        const double hd = 0.5 * dt;
+        const double a2 = small_w ? hd : sh * im, b2 = small_w ? (hd * hd) * 0.5 : (1.0 - ch) * im2;
+        double R1[9], Rm[9];
+        {
+            const double rc[3] = {R[0], R[3], R[6]};
+            double r1c[3], rmc[3], X1[3], X2[3];
+            rot_col2(a1, b1, a2, b2, wh, rc, r1c, rmc);
+            gather_cols(r1c, nx, pv, X1, X2);
+#pragma unroll
+            for (int e = 0; e < 3; e++) { R1[3 * e] = r1c[e]; R1[3 * e + 1] = X1[e]; R1[3 * e + 2] = X2[e]; }
+            gather_cols(rmc, nx, pv, X1, X2);
+#pragma unroll
+            for (int e = 0; e < 3; e++) { Rm[3 * e] = rmc[e]; Rm[3 * e + 1] = X1[e]; Rm[3 * e + 2] = X2[e]; }
+        }
+
+        // ---- closed-form coefficients (CpiV1.h:132-142, 196-238)
+        double f1, f2, f3, f4, d1, d2, d3, d4;
+        {
+            const double dt2 = dt * dt, dt3 = dt2 * dt;
+            if (small_w) {
+                f1 = -(dt3 / 3.0); f2 = (dt2 * dt2) / 8.0; f3 = -(dt2 / 2.0); f4 = dt3 / 6.0;
+                d1 = -(dt3 * dt2 / 15.0); d2 = (dt3 * dt3) / 72.0; d3 = -(dt2 * dt2 / 12.0); d4 = (dt3 * dt2) / 60.0;
+            } else {
+                const double im3 = im2 * im, im4 = im2 * im2, th2 = th * th;
+                f1 = (th * cs_ - sn) * im3;
+                f2 = (th2 - 2.0 * cs_ - 2.0 * th * sn + 2.0) * (0.5 * im4);
+                f3 = -(1.0 - cs_) * im2;
+                f4 = (th - sn) * im3;
+                d1 = (th2 * sn - 3.0 * sn + 3.0 * th * cs_) * (im4 * im);
+                d2 = (th2 - 4.0 * cs_ - 4.0 * th * sn + th2 * cs_ + 4.0) * (im4 * im2);
+                d3 = (2.0 * (cs_ - 1.0) + th * sn) * im4;
+                d4 = (2.0 * th + th * cs_ - 3.0 * sn) * (im4 * im);
+            }
+        }
+        // [w x] and [w x]^2, column 0:  W[:,0] = (0, w2, -w1),  W2[:,0] = (-(w1^2 + w2^2), w0 w1, w0 w2)
+        const double Wc[3] = {0.0, wh[2], -wh[1]};
+        const double W2c[3] = {-(wh[1] * wh[1] + wh[2] * wh[2]), wh[0] * wh[1], wh[0] * wh[2]};
+        const double hdt2 = (dt * dt) * 0.5;
+        double Wa[3], W2a[3], ua[3], ub[3];
+        cross(wh, ah, Wa);                                           // W a
+        cross(wh, Wa, W2a);                                          // W^2 a
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            ua[e] = hdt2 * ah[e] + f1 * Wa[e] + f2 * W2a[e];         // alpha_arg * a_hat   (CpiV1.h:145)
+            ub[e] = dt * ah[e] + f3 * Wa[e] + f4 * W2a[e];           // beta_arg * a_hat    (CpiV1.h:146)
+        }
+        const double r1c[3] = {R1[0], R1[3], R1[6]};
+        // alpha += beta dt + R1^T alpha_arg a ;  beta += R1^T beta_arg a      (CpiV1.h:153-154, old beta); this lane owns element c
+        {
+            const double be = FST(FS_BE);
+            FST(FS_AL) = FST(FS_AL) + be * dt + (r1c[0] * ua[0] + r1c[1] * ua[1] + r1c[2] * ua[2]);
+            FST(FS_BE) = be + (r1c[0] * ub[0] + r1c[1] * ub[1] + r1c[2] * ub[2]);
+        }
+
+        if (MODEL == 1) {
+            // ---- analytic bias Jacobians, own column (CpiV1.h:162-259)
+            double aargc[3], bargc[3], Hal[3], Hbe[3], Jq[3], Ja[3], Jb[3], Ha[3], Hb[3];
+#pragma unroll
+            for (int e = 0; e < 3; e++) { Jq[e] = FST(FS_JQ + e); Ja[e] = FST(FS_JA + e); Jb[e] = FST(FS_JB + e); Ha[e] = FST(FS_HA + e); Hb[e] = FST(FS_HB + e); }
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                aargc[e] = ((e == 0) ? hdt2 : 0.0) + f1 * Wc[e] + f2 * W2c[e];
+                bargc[e] = ((e == 0) ? dt : 0.0) + f3 * Wc[e] + f4 * W2c[e];
+            }
+            mvT33(R1, aargc, Hal);                                   // column of R_tau12k * alpha_arg
+            mvT33(R1, bargc, Hbe);
+            {
+                const double ith = small_w ? 0.0 : 1.0 / th;
+                const double c1 = small_w ? 0.5 : (1.0 - cs_) * (ith * ith), c2 = small_w ? (1.0 / 6.0) : (th - sn) * (ith * ith * ith);
+                const double ca = c1 * dt, cb = c2 * dt * dt;        // w_tx = dt W, w_tx^2 = dt^2 W2
+                double t3[3];
+                rot_col(a1, b1, wh, Jq, t3);                         // R_tau2tau1 * J_q
+#pragma unroll
+                for (int e = 0; e < 3; e++) { Jq[e] = t3[e] + (((e == 0) ? 1.0 : 0.0) - ca * Wc[e] + cb * W2c[e]) * dt; FST(FS_JQ + e) = Jq[e]; }   // CpiV1.h:167
+            }
+#pragma unroll
+            for (int e = 0; e < 3; e++) {                            // CpiV1.h:170-172 (old H_b)
+                FST(FS_HA + e) = (Ha[e] - Hal[e]) + dt * Hb[e];
+                FST(FS_HB + e) = Hb[e] - Hbe[e];
+            }
+            {
+                // column 0 of the frame: e_0 x a = (0, -a2, a1)
+                const double exa[3] = {0.0, -ah[2], ah[1]}, exWa[3] = {0.0, -Wa[2], Wa[1]};
+                double Wexa[3], c1v[3], c2v[3], va_[3], vb_[3], oa3[3], ob3[3];
+                cross(wh, exa, Wexa);
+                cross(Jq, ua, c1v);                                  // [J_q e_i x] (alpha_arg a), NEW J_q
+                cross(Jq, ub, c2v);
+                const double wi = wh[0];
+#pragma unroll
+                for (int e = 0; e < 3; e++) {
+                    va_[e] = -c1v[e] + (wi * d1) * Wa[e] - f1 * exa[e] + (wi * d2) * W2a[e] - f2 * (exWa[e] + Wexa[e]);
+                    vb_[e] = -c2v[e] + (wi * d3) * Wa[e] - f3 * exa[e] + (wi * d4) * W2a[e] - f4 * (exWa[e] + Wexa[e]);
+                }
+                mvT33(R1, va_, oa3);
+                mvT33(R1, vb_, ob3);
+#pragma unroll
+                for (int r = 0; r < 3; r++) {                        // J_a += J_b dt (old J_b, CpiV1.h:241) then the column terms
+                    FST(FS_JA + r) = (Ja[r] + Jb[r] * dt) + oa3[r];
+                    FST(FS_JB + r) = Jb[r] + ob3[r];
+                }
+            }
+        }
+        if (MODEL == 2) {
+            // ---- Discrete_J_b <- B_k Phi Discrete_J_b on the consumed columns (CpiV2.h:347-426, 443).  Phi is RK4 on Phi' = F Phi, a
+            // LINEAR map, so it is applied directly to this lane's own columns (bg_c, ba_c, l_c) of Discrete_J_b: same four stages,
+            // no Phi ever formed, nothing crosses lanes.  Rows: theta' = -W theta - e_c (bg column only); v' = A_s theta + C_s theta(start)
+            // (the clone rows equal the theta rows at the start of every step, B_k) + B_s e_c (ba column) + L_s e_c (l column); p' = v.
+            const double hdt = 0.5 * dt, dt6 = dt / 6.0;
+            double xt[3], xv[3], st[3], sv[3], sp[3], gxt0[3];
+            const double Dtg[3] = {FST(FS_DTG), FST(FS_DTG + 1), FST(FS_DTG + 2)}, Dvg[3] = {FST(FS_DVG), FST(FS_DVG + 1), FST(FS_DVG + 2)};
+            cross(g_tau, Dtg, gxt0);                                 // g_tau x theta(start): the C_s term is -R_s^T of this
+#pragma unroll
+            for (int e = 0; e < 3; e++) { xt[e] = Dtg[e]; xv[e] = Dvg[e]; }
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const double* Rs = (s == 0) ? R : (s == 3 ? R1 : Rm);
+                const double cn = (s < 2) ? hdt : dt;
+                double kt[3], u[3], kv[3];
+                cross(xt, wh, kt);
+                kt[0] -= 1.0;
+                cross(ah, xt, u);
+#pragma unroll
+                for (int e = 0; e < 3; e++) u[e] += gxt0[e];
+                negRt(Rs, u, kv);
+#pragma unroll
+                for (int e = 0; e < 3; e++) {
+                    st[e] = (s == 0) ? kt[e] : (s == 3 ? st[e] + kt[e] : st[e] + 2.0 * kt[e]);
+                    sv[e] = (s == 0) ? kv[e] : (s == 3 ? sv[e] + kv[e] : sv[e] + 2.0 * kv[e]);
+                    sp[e] = (s == 0) ? xv[e] : (s == 3 ? sp[e] + xv[e] : sp[e] + 2.0 * xv[e]);
+                    if (s < 3) { xt[e] = Dtg[e] + cn * kt[e]; xv[e] = Dvg[e] + cn * kv[e]; }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                FST(FS_DTG + e) = Dtg[e] + dt6 * st[e];
+                FST(FS_DVG + e) = Dvg[e] + dt6 * sv[e];
+                FST(FS_DPG + e) = FST(FS_DPG + e) + dt6 * sp[e];
+            }
+            // ba and l columns: v' = B_s e_c = -(row 0 of R_s),  v' = L_s e_c = -R_s^T (R_old [g_k x] e_c)  (CpiV2.h:336); p' = v
+            const double gk[3] = {FST(FS_GK), FST(FS_GK + 1), FST(FS_GK + 2)};
+            const double sk0[3] = {0.0, gk[2], -gk[1]};              // [g_k x] e_0
+            double y[3], l0[3], lm[3], l1[3];
+            mv33(R, sk0, y);
+            negRt(R, y, l0); negRt(Rm, y, lm); negRt(R1, y, l1);
+            const double Ppv = dt6 * (1.0 + 2.0 + 2.0 + 1.0);
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                const double b0 = -R[e], bm = -Rm[e], b1 = -R1[e];
+                const double dva = FST(FS_DVA + e), dvl = FST(FS_DVL + e);
+                FST(FS_DPA + e) = dt6 * (2.0 * (b0 * hdt) + 2.0 * (bm * hdt) + bm * dt) + Ppv * dva + FST(FS_DPA + e);
+                FST(FS_DVA + e) = dt6 * (b0 + 2.0 * bm + 2.0 * bm + b1) + dva;
+                FST(FS_DPL + e) = dt6 * (2.0 * (l0[e] * hdt) + 2.0 * (lm[e] * hdt) + lm[e] * dt) + Ppv * dvl + FST(FS_DPL + e);
+                FST(FS_DVL + e) = dt6 * (l0[e] + 2.0 * lm[e] + 2.0 * lm[e] + l1[e]) + dvl;
+            }
+        }
+        CPI_FENCE();
+
+        // ---- covariance RK4 (CpiV1.h:272-353)
+        {
+            T w_[3], a_[3], g_[3], R_[9], Rm_[9], R1_[9];
+#pragma unroll
+            for (int e = 0; e < 3; e++) { w_[e] = (T)wh[e]; a_[e] = (T)ah[e]; g_[e] = (T)g_tau[e]; }
+#pragma unroll
+            for (int e = 0; e < 9; e++) { R_[e] = (T)R[e]; Rm_[e] = (T)Rm[e]; R1_[e] = (T)R1[e]; }
+            const double dt6 = dt / 6.0;
+            tri_cov_step<MODEL, T>(P, sl, w_, a_, g_, R_, Rm_, R1_, (T)pgg, (T)paa, (T)dt, (T)dt6, (T)p.q_w, (T)p.q_wb, (T)p.q_a, (T)p.q_ab, nx, pv);
+            pgg += dt6 * (p.q_wb + 2.0 * p.q_wb + 2.0 * p.q_wb + p.q_wb);
+            paa += dt6 * (p.q_ab + 2.0 * p.q_ab + 2.0 * p.q_ab + p.q_ab);
+        }
+#pragma unroll
+        for (int e = 0; e < 9; e++) R[e] = R1[e];                    // CpiV1.h:357
+    }
+
+    // ---- write the record (column-major 3x3 / 15x15, include/cpi_b200.h).  Lane c writes original column c (rows c, c+1, c+2).
+    // symmetric diagonal blocks: average the two independently rounded copies of each off-diagonal entry (the reference
+    // symmetrises every step, CpiV1.h:353)
+    T sTT[3], sVV[3], sPP[3];
+    sTT[0] = P.TT[0]; sTT[1] = T(0.5) * (P.TT[1] + shf(P.TT[2], nx)); sTT[2] = T(0.5) * (P.TT[2] + shf(P.TT[1], pv));
+    sVV[0] = P.VV[0]; sVV[1] = T(0.5) * (P.VV[1] + shf(P.VV[2], nx)); sVV[2] = T(0.5) * (P.VV[2] + shf(P.VV[1], pv));
+    sPP[0] = P.PP[0]; sPP[1] = T(0.5) * (P.PP[1] + shf(P.PP[2], nx)); sPP[2] = T(0.5) * (P.PP[2] + shf(P.PP[1], pv));
+    if (!active) return;
+    constexpr int RD = (MODEL == 1) ? CPI_REC_V1_DOUBLES : CPI_REC_V2_DOUBLES;
+    T* rec = reinterpret_cast<T*>(p.out) + win * (int64_t)RD;
+    const int ri[3] = {i0, i1, i2};
+    if (c == 0) {                                                    // lane 0's frame is the original frame
+        double q[4];
+        rot_2_quat(R, q);                                            // CpiV1.h:358 (only the last one is ever consumed)
+        rec[CPI_REC_Q] = (T)q[0]; rec[CPI_REC_Q + 1] = (T)q[1]; rec[CPI_REC_Q + 2] = (T)q[2]; rec[CPI_REC_Q + 3] = (T)q[3];
+        rec[CPI_REC_DT] = (T)DT;
+    }
+    rec[CPI_REC_ALPHA + c] = (T)FST(FS_AL); rec[CPI_REC_BETA + c] = (T)FST(FS_BE);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int r = ri[k];
+        rec[CPI_REC_R + r + 3 * c] = (T)R[3 * k];
+        if (MODEL == 1) {
+            rec[CPI_REC_JQ + r + 3 * c] = (T)FST(FS_JQ + k); rec[CPI_REC_JA + r + 3 * c] = (T)FST(FS_JA + k); rec[CPI_REC_JB + r + 3 * c] = (T)FST(FS_JB + k);
+            rec[CPI_REC_HA + r + 3 * c] = (T)FST(FS_HA + k); rec[CPI_REC_HB + r + 3 * c] = (T)FST(FS_HB + k);
+        } else {   // read-out of Discrete_J_b (CpiV2.h:450-458): J_q = -D[theta,bg], J_a = D[p,bg], J_b = D[v,bg], H_a = D[p,ba], H_b = D[v,ba], O_a = D[p,l], O_b = D[v,l]
+            rec[CPI_REC_JQ + r + 3 * c] = (T)(-FST(FS_DTG + k)); rec[CPI_REC_JA + r + 3 * c] = (T)FST(FS_DPG + k); rec[CPI_REC_JB + r + 3 * c] = (T)FST(FS_DVG + k);
+            rec[CPI_REC_HA + r + 3 * c] = (T)FST(FS_DPA + k); rec[CPI_REC_HB + r + 3 * c] = (T)FST(FS_DVA + k);
+            rec[CPI_REC_OA + r + 3 * c] = (T)FST(FS_DPL + k); rec[CPI_REC_OB + r + 3 * c] = (T)FST(FS_DVL + k);
+        }
+    }
+    // P_meas, full 15x15: block (I,J), I,J in {theta=0, bg=1, v=2, ba=3, p=4}; every off-diagonal block is written twice
+    T* Pm = rec + CPI_REC_P;
+    auto put2 = [&](int I, int J, int r, T v) { Pm[(3 * I + r) + 15 * (3 * J + c)] = v; Pm[(3 * J + c) + 15 * (3 * I + r)] = v; };
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int r = ri[k];
+        put2(0, 0, r, sTT[k]); put2(2, 2, r, sVV[k]); put2(4, 4, r, sPP[k]);
+        put2(0, 1, r, P.TG[k]); put2(1, 2, r, P.GV[k]); put2(0, 2, r, P.TV[k]); put2(3, 2, r, P.AV[k]);
+        put2(0, 4, r, P.TP[k]); put2(1, 4, r, P.GP[k]); put2(3, 4, r, P.AP[k]); put2(2, 4, r, P.VP[k]);
+        put2(1, 1, r, r == c ? (T)pgg : T(0)); put2(3, 3, r, r == c ? (T)paa : T(0));
+        put2(0, 3, r, T(0)); put2(1, 3, r, T(0));                    // P_theta,ba = P_bg,ba = 0 identically
+    }
+}
+
+#undef SLT
+#undef FST
+#undef CN
+#undef KSUM
+
+template <int MODEL, class T>
+static cudaError_t launch_tri_one(const PreintParams& p0, int num_sms, cudaStream_t st) {
+    PreintParams p = p0;
+    auto kern = k_preintegrate_tri<MODEL, T>;
+    constexpr int smem = (int)TriSmem<MODEL, T>::bytes;
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        if (dev < 64) configured[dev] = true;
+    }
+    // windows per block: one wave over all SMs if the batch fits (latency-bound regime), else the CTA capacity
+    const int64_t need = (p.n_windows + num_sms - 1) / num_sms;
+    if (p.wpb <= 0 || p.wpb > TRI_WPB) p.wpb = (int)(need <= TRI_WPB ? (need < 1 ? 1 : need) : TRI_WPB);
+    const int grid = (int)((p.n_windows + p.wpb - 1) / p.wpb);
+    kern<<<grid, TRI_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+int preint_tri_cap() { return TRI_WPB; }
+bool preint_tri_supported(int model, int flags) {
+    if (flags & CPI_FLAG_IMU_AVG) return false;
+    return model == 1 || (model == 2 && !(flags & CPI_FLAG_ANALYTIC_JACOBIANS));
+}
+
+cudaError_t preint_launch_tri(int model, int dtype, const PreintParams& p, int num_sms, cudaStream_t st) {
+    if (model == 1) return dtype == 32 ? launch_tri_one<1, float>(p, num_sms, st) : launch_tri_one<1, double>(p, num_sms, st);
+    if (model == 2) return dtype == 32 ? launch_tri_one<2, float>(p, num_sms, st) : launch_tri_one<2, double>(p, num_sms, st);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace cpi
