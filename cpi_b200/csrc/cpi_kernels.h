@@ -33,7 +33,7 @@ int preint_ws_cap(int dtype);
 int preint_cap(int model, int dtype, int flags, int num_sms);
 // tri-lane kernels (preintegrate_tri.cu)
 bool preint_tri_supported(int model, int flags);
-int preint_tri_cap();
+int preint_tri_cap(int model, int dtype);
 cudaError_t preint_launch_tri(int model, int dtype, const PreintParams& p, int num_sms, cudaStream_t st);
 cudaError_t preint_launch(int model, int dtype, int flags, const PreintParams& p0, int num_sms, int max_smem_bytes, cudaStream_t st, int* launches);
 cudaError_t factor_launch(int model, const FactorParams& p, cudaStream_t st);

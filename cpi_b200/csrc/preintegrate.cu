@@ -1284,7 +1284,7 @@ int preint_ws_cap(int dtype) { return dtype == 32 ? TileWS<float>::S : TileWS<do
 static bool use_legacy() { static const bool v = getenv("CPI_B200_LEGACY") != nullptr || getenv("CPI_B200_FUSED") != nullptr; return v; }
 
 int preint_cap(int model, int dtype, int flags, int num_sms) {
-    if (!use_legacy() && preint_tri_supported(model, flags)) return preint_tri_cap();
+    if (!use_legacy() && preint_tri_supported(model, flags)) return preint_tri_cap(model, dtype);
     if (model == 1 && !(flags & CPI_FLAG_IMU_AVG) && getenv("CPI_B200_FUSED") == nullptr) return preint_ws_cap(dtype);
     return preint_pick_wpb(model, dtype, (int64_t)1 << 40, num_sms);
 }

@@ -30,9 +30,14 @@
 namespace cpi {
 
 constexpr int TRI_WPW = 10;                 // windows per warp (lanes 30, 31 idle)
-constexpr int TRI_THREADS = 256;            // CTA size (compile-time: slot stride)
-constexpr int TRI_WPB = TRI_WPW * TRI_THREADS / 32;   // window slots per CTA
-constexpr int TRI_BUF_STRIDE = 272;         // bytes of sample staging per window: 2 x 128 B + 16 B pad (bank spread; 16-B aligned for TMA)
+// CTA size (compile-time: it is the stride of the lane-private shared-memory slots).  Model 2 in fp64 needs 60 + 32 slot doubles per
+// lane, which fits 227 KB at 224 threads (7 warps, 70 windows) only.
+template <int MODEL, class T> struct TriNT { static constexpr int NT = 256; };
+template <> struct TriNT<2, double> { static constexpr int NT = 224; };
+constexpr int TRI_NBUF = 4;                 // 128-byte chunk buffers per window (TMA ring)
+constexpr int TRI_BUF_STRIDE = TRI_NBUF * 128 + 16;   // bytes of sample staging per window, + 16 B pad (bank spread; 16-B aligned for TMA)
+// doubles per window of pre-pass scalars: 3 samples x 16 (model 1: 14 used) or 3 x 8 (model 2), padded to an odd stride (bank spread)
+template <int MODEL> struct TriSC { static constexpr int PER = (MODEL == 1) ? 16 : 8, STRIDE = 3 * PER + 1 + (MODEL == 1 ? 2 : 0); };
 
 template <class T> CPI_DEV T shf(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
@@ -54,14 +59,20 @@ template <int MODEL> struct TriL {
 enum : int { FS_BW = 0, FS_BA = 3, FS_AL = 6, FS_BE = 7, FS_JQ = 8, FS_JA = 11, FS_JB = 14, FS_HA = 17, FS_HB = 20,
              FS_GK = 8, FS_DTG = 11, FS_DVG = 14, FS_DPG = 17, FS_DVA = 20, FS_DPA = 23, FS_DVL = 26, FS_DPL = 29 };
 template <int MODEL, class T> struct TriSmem {
-    static constexpr size_t off_fs = (size_t)TriL<MODEL>::NSL * TRI_THREADS * sizeof(T);
-    static constexpr size_t off_buf = off_fs + (size_t)TriL<MODEL>::NFS * TRI_THREADS * 8;
-    static constexpr size_t off_bar = off_buf + (size_t)TRI_WPB * TRI_BUF_STRIDE;
-    static constexpr size_t bytes = off_bar + (size_t)TRI_WPB * 16;
+    static constexpr int NT = TriNT<MODEL, T>::NT;
+    static constexpr int WPB = TRI_WPW * NT / 32;                     // window slots per CTA
+    static constexpr size_t off_fs = (size_t)TriL<MODEL>::NSL * NT * sizeof(T);
+    static constexpr size_t off_sc = off_fs + (size_t)TriL<MODEL>::NFS * NT * 8;
+    // scalar sets: one slot per window + one dummy slot per warp for the two idle lanes
+    static constexpr size_t off_buf = (off_sc + (size_t)(WPB + NT / 32) * TriSC<MODEL>::STRIDE * 8 + 127) / 128 * 128;
+    static constexpr size_t off_bar = off_buf + (size_t)WPB * TRI_BUF_STRIDE;
+    static constexpr size_t bytes = off_bar + (size_t)WPB * 8 * TRI_NBUF;
 };
+static_assert(TriSmem<1, double>::bytes <= 232448 && TriSmem<2, double>::bytes <= 232448 && TriSmem<1, float>::bytes <= 232448 &&
+              TriSmem<2, float>::bytes <= 232448, "tri-lane smem layout exceeds 227 KB");
 
-#define SLT(e) sl[(e) * TRI_THREADS]
-#define FST(e) fs[(e) * TRI_THREADS]
+#define SLT(e) sl[(e) * NT]
+#define FST(e) fs[(e) * NT]
 #define CN(s) ((s) < 2 ? hdt : dt)                       /* x_{s+2} = x_1 + CN(s) k_{s+1}:  dt/2, dt/2, dt   (CpiV1.h:312, 323, 344) */
 #define KSUM(ks, k, s) ((s) == 0 ? (k) : ((s) == 3 ? (ks) + (k) : fma(T(2), (k), (ks))))   /* ((k1 + 2 k2) + 2 k3) + k4  (CpiV1.h:352) */
 #define CPI_FENCE() asm volatile("" ::: "memory")
@@ -79,7 +90,7 @@ template <class T> struct TriP {
 
 // One RK4 step of the covariance (model 1: CpiV1.h:272-353).  w, ah: estimated readings; R, Rm, R1: old / mid / new
 // rotation (row-major, lane frame); pgg, paa: the scalar diagonal blocks P_bg,bg and P_ba,ba at the start of the step.
-template <int MODEL, class T>
+template <int MODEL, int NT, class T>
 CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, const T* w, const T* ah, const T* gt, const T* R, const T* Rm, const T* R1, T pgg, T paa, T dt, T dt6,
                           T q_w, T q_wb, T q_a, T q_ab, int nx, int pv) {
     const T hdt = dt * T(0.5);
@@ -290,10 +301,16 @@ CPI_DEV void rot_col(double a, double b, const double* w, const double* v, doubl
     for (int e = 0; e < 3; e++) o[e] = (v[e] - a * t[e]) + b * u[e];
 }
 
+// Scalars of one sample that depend on the raw sample and the bias only -- NOT on the recurrence (CpiV1.h:97-142, 162-164, 196-238):
+// rotation coefficients of the full and the half step, f1..f4, and (model 1) the d f/d|w| terms and the right-Jacobian coefficients.
+enum : int { SC_A1 = 0, SC_B1, SC_A2, SC_B2, SC_F1, SC_F2, SC_F3, SC_F4, SC_D1, SC_D2, SC_D3, SC_D4, SC_CA, SC_CB, SC_N };
+
 template <int MODEL, class T>
-__global__ void __launch_bounds__(TRI_THREADS, 1) k_preintegrate_tri(const PreintParams p) {
+__global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(const PreintParams p) {
     using SM_ = TriSmem<MODEL, T>;
+    constexpr int NT = SM_::NT;
     constexpr int CH = 8 / (int)sizeof(T) * 2;            // samples per TMA chunk: 2 (fp64) or 4 (fp32) = 112 B in one aligned 128-B fetch
+    constexpr int EPC = 128 / (int)sizeof(T);             // elements per chunk buffer
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool lane_ok = lane < 3 * TRI_WPW;
@@ -308,16 +325,21 @@ __global__ void __launch_bounds__(TRI_THREADS, 1) k_preintegrate_tri(const Prein
 
     T* sl = reinterpret_cast<T*>(smem_raw) + threadIdx.x;
     double* fs = reinterpret_cast<double*>(smem_raw + SM_::off_fs) + threadIdx.x;
+    // per-window scalar sets of the current 3 samples (the two idle lanes of a warp get a dummy slot of their own)
+    double* sc = reinterpret_cast<double*>(smem_raw + SM_::off_sc) + (size_t)(lane_ok ? wslot : SM_::WPB + wid) * TriSC<MODEL>::STRIDE;
     const T* buf = reinterpret_cast<const T*>(smem_raw + SM_::off_buf + (size_t)wslot * TRI_BUF_STRIDE);
     const uint32_t buf0 = smem_u32(buf);
-    const uint32_t bar0 = smem_u32(smem_raw + SM_::off_bar + (size_t)wslot * 16);
+    const uint32_t bar0 = smem_u32(smem_raw + SM_::off_bar + (size_t)wslot * (8 * TRI_NBUF));
 
     // ---- per-window constants (setLinearizationPoints, CpiBase.h:73-80), in the lane frame
-    int64_t o0 = 0, nsteps = 0;
+    int64_t o0 = 0;
+    int nsteps = 0;
 #pragma unroll
     for (int e = 0; e < TriL<MODEL>::NFS; e++) FST(e) = 0.0;
+    double bwo[3] = {0, 0, 0};                                       // gyro bias in the ORIGINAL axis order (|w_hat| is summed in that order)
     if (active) {
         const T* lin = reinterpret_cast<const T*>(p.lin) + win * CPI_LIN_DOUBLES;
+        bwo[0] = (double)lin[0]; bwo[1] = (double)lin[1]; bwo[2] = (double)lin[2];
         FST(FS_BW) = (double)lin[i0]; FST(FS_BW + 1) = (double)lin[i1]; FST(FS_BW + 2) = (double)lin[i2];
         FST(FS_BA) = (double)lin[3 + i0]; FST(FS_BA + 1) = (double)lin[3 + i1]; FST(FS_BA + 2) = (double)lin[3 + i2];
         if (MODEL == 2) {                                            // g_k = quat_2_Rot(q_k_lin) * grav  (CpiV2.h:99, 202, 315), rotated into the lane frame
@@ -329,28 +351,47 @@ __global__ void __launch_bounds__(TRI_THREADS, 1) k_preintegrate_tri(const Prein
             FST(FS_GK + 1) = c == 0 ? gk[1] : (c == 1 ? gk[2] : gk[0]);
             FST(FS_GK + 2) = c == 0 ? gk[2] : (c == 1 ? gk[0] : gk[1]);
         }
-        if (p.offsets) { o0 = p.offsets[win]; nsteps = p.offsets[win + 1] - o0; }
-        else { o0 = win * p.ns_uniform; nsteps = p.ns_uniform; }
-        if (nsteps < 0) nsteps = 0;
+        int64_t ns64;
+        if (p.offsets) { o0 = p.offsets[win]; ns64 = p.offsets[win + 1] - o0; }
+        else { o0 = win * p.ns_uniform; ns64 = p.ns_uniform; }
+        nsteps = ns64 < 0 ? 0 : (ns64 > 2147483000 ? 2147483000 : (int)ns64);
     }
     const T* sp = reinterpret_cast<const T*>(p.samples) + o0 * CPI_SAMPLE_DOUBLES;
-    const int wmax = __reduce_max_sync(0xffffffffu, (int)nsteps);
+    const int wmax = __reduce_max_sync(0xffffffffu, nsteps);
 
-    // ---- TMA pipeline: lane 0 of the trio stages the window's stream, two 128-byte chunks in flight
+    // ---- TMA pipeline: lane 0 of the trio stages the window's stream through a ring of TRI_NBUF 128-byte chunk buffers.  Chunk k
+    // (samples CH k .. CH k + CH - 1, fetched as ONE aligned 128-byte transaction that also absorbs the misalignment of the
+    // window start) lives in buffer k % NBUF, completes phase k / NBUF of barrier k % NBUF.  The last samples of a window are
+    // read with plain loads: an aligned 128-byte fetch there could run past the caller's buffer.
     const int shift = (int)(((uintptr_t)sp & 15) / sizeof(T));      // misalignment of the window start w.r.t. 16 bytes, in elements
-    const int64_t n_tma = nsteps > 0 ? (nsteps - 1) / CH : 0;       // chunks with at least one more sample after them
+    const int n_tma = nsteps > 0 ? (nsteps - 1) / CH : 0;           // chunks with at least one more sample after them
+    const int n_tma_samples = n_tma * CH;
+    int next_issue = 0;
     if (active && c == 0) {
-        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+#pragma unroll
+        for (int k = 0; k < TRI_NBUF; k++) mbar_init(bar0 + 8 * k, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
 #pragma unroll
-        for (int k = 0; k < 2; k++)
+        for (int k = 0; k < TRI_NBUF; k++)
             if (k < n_tma) {
                 mbar_arrive_expect_tx(bar0 + 8 * k, 128);
                 bulk_g2s(buf0 + 128 * k, sp + 7 * CH * k - shift, 128, bar0 + 8 * k);
             }
+        next_issue = TRI_NBUF;
     }
     __syncwarp();                                                    // barrier init visible to the trio before anyone polls
+
+    // pointer to sample `is` of this window: staged copy (after waiting for its chunk) or global memory (tail); null steps return nullptr
+    auto sample_ptr = [&](int is, bool& from_smem) -> const T* {
+        from_smem = is < n_tma_samples;
+        if (from_smem) {
+            const int k = is / CH, b = k % TRI_NBUF;
+            mbar_wait(bar0 + 8 * b, (uint32_t)((k / TRI_NBUF) & 1));
+            return buf + b * EPC + shift + 7 * (is % CH);
+        }
+        return sp + (int64_t)is * CPI_SAMPLE_DOUBLES;
+    };
 
     // ---- state (CpiBase.h:99-124 initialisers), lane frame
     double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};                       // full old rotation, row-major
@@ -360,229 +401,254 @@ __global__ void __launch_bounds__(TRI_THREADS, 1) k_preintegrate_tri(const Prein
     for (int e = 0; e < 3; e++) P.TG[e] = P.TT[e] = P.GV[e] = P.TV[e] = P.AV[e] = P.VV[e] = P.TP[e] = P.GP[e] = P.AP[e] = P.VP[e] = P.PP[e] = T(0);
 
 #pragma unroll 1
-    for (int it = 0; it < wmax; it++) {
-        // ---- fetch entry `it` in the lane frame; finished windows run a NULL step (dt = 0: an exact no-op, see below)
-        double wm[3] = {0, 0, 0}, am[3] = {0, 0, 0}, dt = 0.0;
-        if (it < nsteps) {
-            if (it < CH * n_tma) {
-                const int64_t ck = it / CH;
-                const int b = (int)(ck & 1), j = (int)(it % CH);
-                if (j == 0) {
-                    mbar_wait(bar0 + 8 * b, (uint32_t)((ck >> 1) & 1));
-                    // the other buffer (chunk ck-1) has been consumed by all three lanes: refill it with chunk ck+1
-                    if (c == 0 && ck >= 1 && ck + 1 < n_tma) {
-                        fence_proxy_async();
-                        mbar_arrive_expect_tx(bar0 + 8 * (b ^ 1), 128);
-                        bulk_g2s(buf0 + 128 * (b ^ 1), sp + 7 * CH * (ck + 1) - shift, 128, bar0 + 8 * (b ^ 1));
-                    }
-                }
-                const T* src = buf + b * (128 / (int)sizeof(T)) + shift + 7 * j;
-                wm[0] = (double)src[i0]; wm[1] = (double)src[i1]; wm[2] = (double)src[i2];
-                am[0] = (double)src[3 + i0]; am[1] = (double)src[3 + i1]; am[2] = (double)src[3 + i2];
-                dt = (double)src[6];
-            } else {
-                const T* src = sp + (int64_t)it * CPI_SAMPLE_DOUBLES;
-                wm[0] = (double)__ldg(src + i0); wm[1] = (double)__ldg(src + i1); wm[2] = (double)__ldg(src + i2);
-                am[0] = (double)__ldg(src + 3 + i0); am[1] = (double)__ldg(src + 3 + i1); am[2] = (double)__ldg(src + 3 + i2);
-                dt = (double)__ldg(src + 6);
+    for (int it0 = 0; it0 < wmax; it0 += 3) {
+        // ================= pre-pass: lane c evaluates the recurrence-free scalars of sample it0 + c =================
+        // (one sincos pair, one reciprocal and the closed-form coefficient functions per LANE instead of per lane and sample)
+        {
+            const int is = it0 + c;
+            double w0 = 0.0, w1 = 0.0, w2 = 0.0, dt = 0.0;
+            if (is < nsteps) {
+                bool sm_;
+                const T* src = sample_ptr(is, sm_);
+                if (sm_) { w0 = (double)src[0]; w1 = (double)src[1]; w2 = (double)src[2]; dt = (double)src[6]; }
+                else { w0 = (double)__ldg(src); w1 = (double)__ldg(src + 1); w2 = (double)__ldg(src + 2); dt = (double)__ldg(src + 6); }
             }
-        }
-        DT += dt;                                                    // CpiV1.h:69 (before the dt == 0 return)
-
-        // ---- estimated readings (CpiV1.h:77-86)
-        const double wh[3] = {wm[0] - FST(FS_BW), wm[1] - FST(FS_BW + 1), wm[2] - FST(FS_BW + 2)};
-        double ah[3] = {am[0] - FST(FS_BA), am[1] - FST(FS_BA + 1), am[2] - FST(FS_BA + 2)};
-        double g_tau[3] = {0.0, 0.0, 0.0};
-        if (MODEL == 2) {                                            // a_hat = a_m - b_a - R_k2tau R_G2k g  with the OLD rotation (CpiV2.h:99)
-            const double gk[3] = {FST(FS_GK), FST(FS_GK + 1), FST(FS_GK + 2)};
-            mv33(R, gk, g_tau);
-            ah[0] -= g_tau[0]; ah[1] -= g_tau[1]; ah[2] -= g_tau[2];
-        }
-        const double mag2 = wh[0] * wh[0] + wh[1] * wh[1] + wh[2] * wh[2];
-        const double mag = sqrt(mag2);
-        const double th = mag * dt;
-        // CpiV1.h:101.  dt == 0 is the reference's silent no-op (CpiV1.h:72-74); the Taylor branch at dt = 0 gives exactly that
-        // (D = I, every coefficient 0), so null steps need no branch around the shuffles below.
-        const bool small_w = mag < 0.008726646 || dt == 0.0;
-        double sn, cs_, sh, ch;
-        sincos(th, &sn, &cs_);
-        sincos(mag * 0.5 * dt, &sh, &ch);
-        const double im = small_w ? 0.0 : 1.0 / mag;
-        const double im2 = im * im;
-
-        // ---- relative rotation: own column of the new and the mid-point rotation (CpiV1.h:119-124, 267-269), then the full matrices
-        const double a1 = small_w ? dt : sn * im, b1 = small_w ? (dt * dt) * 0.5 : (1.0 - cs_) * im2;
-        const double hd = 0.5 * dt;
-        const double a2 = small_w ? hd : sh * im, b2 = small_w ? (hd * hd) * 0.5 : (1.0 - ch) * im2;
-        double R1[9], Rm[9];
-        {
-            const double rc[3] = {R[0], R[3], R[6]};
-            double r1c[3], rmc[3], X1[3], X2[3];
-            rot_col2(a1, b1, a2, b2, wh, rc, r1c, rmc);
-            gather_cols(r1c, nx, pv, X1, X2);
-#pragma unroll
-            for (int e = 0; e < 3; e++) { R1[3 * e] = r1c[e]; R1[3 * e + 1] = X1[e]; R1[3 * e + 2] = X2[e]; }
-            gather_cols(rmc, nx, pv, X1, X2);
-#pragma unroll
-            for (int e = 0; e < 3; e++) { Rm[3 * e] = rmc[e]; Rm[3 * e + 1] = X1[e]; Rm[3 * e + 2] = X2[e]; }
-        }
-
-        // ---- closed-form coefficients (CpiV1.h:132-142, 196-238)
-        double f1, f2, f3, f4, d1, d2, d3, d4;
-        {
+            w0 -= bwo[0]; w1 -= bwo[1]; w2 -= bwo[2];                // CpiV1.h:77-79
+            const double mag = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+            const double th = mag * dt;
+            // CpiV1.h:101.  dt == 0 is the reference's silent no-op (CpiV1.h:72-74); the Taylor branch at dt = 0 gives exactly that
+            // (D = I, every coefficient 0), so null steps (finished windows, dt = 0 samples) need no branch around the shuffles.
+            const bool small_w = mag < 0.008726646 || dt == 0.0;
+            double sn, cs_, sh, ch;
+            sincos(th, &sn, &cs_);
+            sincos(mag * 0.5 * dt, &sh, &ch);
+            const double im = small_w ? 0.0 : 1.0 / mag;             // one reciprocal instead of ~16 divisions; never used when small_w
+            const double im2 = im * im;
+            const double hd = 0.5 * dt;
+            double v[SC_N];
+            v[SC_A1] = small_w ? dt : sn * im; v[SC_B1] = small_w ? (dt * dt) * 0.5 : (1.0 - cs_) * im2;      // CpiV1.h:119-120
+            v[SC_A2] = small_w ? hd : sh * im; v[SC_B2] = small_w ? (hd * hd) * 0.5 : (1.0 - ch) * im2;       // CpiV1.h:267-268
             const double dt2 = dt * dt, dt3 = dt2 * dt;
-            if (small_w) {
-                f1 = -(dt3 / 3.0); f2 = (dt2 * dt2) / 8.0; f3 = -(dt2 / 2.0); f4 = dt3 / 6.0;
-                d1 = -(dt3 * dt2 / 15.0); d2 = (dt3 * dt3) / 72.0; d3 = -(dt2 * dt2 / 12.0); d4 = (dt3 * dt2) / 60.0;
+            if (small_w) {                                           // CpiV1.h:132-142, 196-238
+                v[SC_F1] = -(dt3 / 3.0); v[SC_F2] = (dt2 * dt2) / 8.0; v[SC_F3] = -(dt2 / 2.0); v[SC_F4] = dt3 / 6.0;
+                v[SC_D1] = -(dt3 * dt2 / 15.0); v[SC_D2] = (dt3 * dt3) / 72.0; v[SC_D3] = -(dt2 * dt2 / 12.0); v[SC_D4] = (dt3 * dt2) / 60.0;
+                v[SC_CA] = 0.5 * dt; v[SC_CB] = (1.0 / 6.0) * dt * dt;
             } else {
                 const double im3 = im2 * im, im4 = im2 * im2, th2 = th * th;
-                f1 = (th * cs_ - sn) * im3;
-                f2 = (th2 - 2.0 * cs_ - 2.0 * th * sn + 2.0) * (0.5 * im4);
-                f3 = -(1.0 - cs_) * im2;
-                f4 = (th - sn) * im3;
-                d1 = (th2 * sn - 3.0 * sn + 3.0 * th * cs_) * (im4 * im);
-                d2 = (th2 - 4.0 * cs_ - 4.0 * th * sn + th2 * cs_ + 4.0) * (im4 * im2);
-                d3 = (2.0 * (cs_ - 1.0) + th * sn) * im4;
-                d4 = (2.0 * th + th * cs_ - 3.0 * sn) * (im4 * im);
+                v[SC_F1] = (th * cs_ - sn) * im3;
+                v[SC_F2] = (th2 - 2.0 * cs_ - 2.0 * th * sn + 2.0) * (0.5 * im4);
+                v[SC_F3] = -(1.0 - cs_) * im2;
+                v[SC_F4] = (th - sn) * im3;
+                if (MODEL == 1) {
+                    v[SC_D1] = (th2 * sn - 3.0 * sn + 3.0 * th * cs_) * (im4 * im);
+                    v[SC_D2] = (th2 - 4.0 * cs_ - 4.0 * th * sn + th2 * cs_ + 4.0) * (im4 * im2);
+                    v[SC_D3] = (2.0 * (cs_ - 1.0) + th * sn) * im4;
+                    v[SC_D4] = (2.0 * th + th * cs_ - 3.0 * sn) * (im4 * im);
+                    const double ith = 1.0 / th;                     // right Jacobian of w dt (CpiV1.h:162-164): w_tx = dt W, w_tx^2 = dt^2 W2
+                    v[SC_CA] = ((1.0 - cs_) * (ith * ith)) * dt; v[SC_CB] = ((th - sn) * (ith * ith * ith)) * dt * dt;
+                }
             }
-        }
-        // [w x] and [w x]^2, column 0:  W[:,0] = (0, w2, -w1),  W2[:,0] = (-(w1^2 + w2^2), w0 w1, w0 w2)
-        const double Wc[3] = {0.0, wh[2], -wh[1]};
-        const double W2c[3] = {-(wh[1] * wh[1] + wh[2] * wh[2]), wh[0] * wh[1], wh[0] * wh[2]};
-        const double hdt2 = (dt * dt) * 0.5;
-        double Wa[3], W2a[3], ua[3], ub[3];
-        cross(wh, ah, Wa);                                           // W a
-        cross(wh, Wa, W2a);                                          // W^2 a
+            constexpr int NSC = (MODEL == 1) ? (int)SC_N : (int)SC_D1;
 #pragma unroll
-        for (int e = 0; e < 3; e++) {
-            ua[e] = hdt2 * ah[e] + f1 * Wa[e] + f2 * W2a[e];         // alpha_arg * a_hat   (CpiV1.h:145)
-            ub[e] = dt * ah[e] + f3 * Wa[e] + f4 * W2a[e];           // beta_arg * a_hat    (CpiV1.h:146)
+            for (int e = 0; e < NSC; e++) sc[c * TriSC<MODEL>::PER + e] = v[e];
         }
-        const double r1c[3] = {R1[0], R1[3], R1[6]};
-        // alpha += beta dt + R1^T alpha_arg a ;  beta += R1^T beta_arg a      (CpiV1.h:153-154, old beta); this lane owns element c
-        {
-            const double be = FST(FS_BE);
-            FST(FS_AL) = FST(FS_AL) + be * dt + (r1c[0] * ua[0] + r1c[1] * ua[1] + r1c[2] * ua[2]);
-            FST(FS_BE) = be + (r1c[0] * ub[0] + r1c[1] * ub[1] + r1c[2] * ub[2]);
-        }
+        __syncwarp();
 
-        if (MODEL == 1) {
-            // ---- analytic bias Jacobians, own column (CpiV1.h:162-259)
-            double aargc[3], bargc[3], Hal[3], Hbe[3], Jq[3], Ja[3], Jb[3], Ha[3], Hb[3];
+#pragma unroll 1
+        for (int j = 0; j < 3; j++) {
+            const int it = it0 + j;
+            if (it >= wmax) break;                                   // warp-uniform
+            // ---- fetch entry `it` in the lane frame; finished windows run a NULL step
+            double wm[3] = {0, 0, 0}, am[3] = {0, 0, 0}, dt = 0.0;
+            if (it < nsteps) {
+                bool sm_;
+                const T* src = sample_ptr(it, sm_);
+                if (sm_) {
+                    wm[0] = (double)src[i0]; wm[1] = (double)src[i1]; wm[2] = (double)src[i2];
+                    am[0] = (double)src[3 + i0]; am[1] = (double)src[3 + i1]; am[2] = (double)src[3 + i2];
+                    dt = (double)src[6];
+                } else {
+                    wm[0] = (double)__ldg(src + i0); wm[1] = (double)__ldg(src + i1); wm[2] = (double)__ldg(src + i2);
+                    am[0] = (double)__ldg(src + 3 + i0); am[1] = (double)__ldg(src + 3 + i1); am[2] = (double)__ldg(src + 3 + i2);
+                    dt = (double)__ldg(src + 6);
+                }
+            }
+            DT += dt;                                                // CpiV1.h:69 (before the dt == 0 return)
+            const double* scj = sc + j * TriSC<MODEL>::PER;
+            const double a1 = scj[SC_A1], b1 = scj[SC_B1], a2 = scj[SC_A2], b2 = scj[SC_B2];
+            const double f1 = scj[SC_F1], f2 = scj[SC_F2], f3 = scj[SC_F3], f4 = scj[SC_F4];
+
+            // ---- estimated readings (CpiV1.h:77-86)
+            const double wh[3] = {wm[0] - FST(FS_BW), wm[1] - FST(FS_BW + 1), wm[2] - FST(FS_BW + 2)};
+            double ah[3] = {am[0] - FST(FS_BA), am[1] - FST(FS_BA + 1), am[2] - FST(FS_BA + 2)};
+            double g_tau[3] = {0.0, 0.0, 0.0};
+            if (MODEL == 2) {                                        // a_hat = a_m - b_a - R_k2tau R_G2k g  with the OLD rotation (CpiV2.h:99)
+                const double gk[3] = {FST(FS_GK), FST(FS_GK + 1), FST(FS_GK + 2)};
+                mv33(R, gk, g_tau);
+                ah[0] -= g_tau[0]; ah[1] -= g_tau[1]; ah[2] -= g_tau[2];
+            }
+
+            // ---- relative rotation: own column of the new and the mid-point rotation (CpiV1.h:119-124, 267-269), then the full matrices
+            double R1[9], Rm[9];
+            {
+                const double rc[3] = {R[0], R[3], R[6]};
+                double r1c[3], rmc[3], X1[3], X2[3];
+                rot_col2(a1, b1, a2, b2, wh, rc, r1c, rmc);
+                gather_cols(r1c, nx, pv, X1, X2);
 #pragma unroll
-            for (int e = 0; e < 3; e++) { Jq[e] = FST(FS_JQ + e); Ja[e] = FST(FS_JA + e); Jb[e] = FST(FS_JB + e); Ha[e] = FST(FS_HA + e); Hb[e] = FST(FS_HB + e); }
+                for (int e = 0; e < 3; e++) { R1[3 * e] = r1c[e]; R1[3 * e + 1] = X1[e]; R1[3 * e + 2] = X2[e]; }
+                gather_cols(rmc, nx, pv, X1, X2);
+#pragma unroll
+                for (int e = 0; e < 3; e++) { Rm[3 * e] = rmc[e]; Rm[3 * e + 1] = X1[e]; Rm[3 * e + 2] = X2[e]; }
+            }
+
+            // ---- means (CpiV1.h:145-154):  alpha += beta dt + R1^T alpha_arg a ;  beta += R1^T beta_arg a   (old beta); this lane owns element c
+            const double hdt2 = (dt * dt) * 0.5;
+            double Wa[3], W2a[3], ua[3], ub[3];
+            cross(wh, ah, Wa);                                       // W a
+            cross(wh, Wa, W2a);                                      // W^2 a
 #pragma unroll
             for (int e = 0; e < 3; e++) {
-                aargc[e] = ((e == 0) ? hdt2 : 0.0) + f1 * Wc[e] + f2 * W2c[e];
-                bargc[e] = ((e == 0) ? dt : 0.0) + f3 * Wc[e] + f4 * W2c[e];
-            }
-            mvT33(R1, aargc, Hal);                                   // column of R_tau12k * alpha_arg
-            mvT33(R1, bargc, Hbe);
-            {
-                const double ith = small_w ? 0.0 : 1.0 / th;
-                const double c1 = small_w ? 0.5 : (1.0 - cs_) * (ith * ith), c2 = small_w ? (1.0 / 6.0) : (th - sn) * (ith * ith * ith);
-                const double ca = c1 * dt, cb = c2 * dt * dt;        // w_tx = dt W, w_tx^2 = dt^2 W2
-                double t3[3];
-                rot_col(a1, b1, wh, Jq, t3);                         // R_tau2tau1 * J_q
-#pragma unroll
-                for (int e = 0; e < 3; e++) { Jq[e] = t3[e] + (((e == 0) ? 1.0 : 0.0) - ca * Wc[e] + cb * W2c[e]) * dt; FST(FS_JQ + e) = Jq[e]; }   // CpiV1.h:167
-            }
-#pragma unroll
-            for (int e = 0; e < 3; e++) {                            // CpiV1.h:170-172 (old H_b)
-                FST(FS_HA + e) = (Ha[e] - Hal[e]) + dt * Hb[e];
-                FST(FS_HB + e) = Hb[e] - Hbe[e];
+                ua[e] = hdt2 * ah[e] + f1 * Wa[e] + f2 * W2a[e];     // alpha_arg * a_hat   (CpiV1.h:145)
+                ub[e] = dt * ah[e] + f3 * Wa[e] + f4 * W2a[e];       // beta_arg * a_hat    (CpiV1.h:146)
             }
             {
-                // column 0 of the frame: e_0 x a = (0, -a2, a1)
-                const double exa[3] = {0.0, -ah[2], ah[1]}, exWa[3] = {0.0, -Wa[2], Wa[1]};
-                double Wexa[3], c1v[3], c2v[3], va_[3], vb_[3], oa3[3], ob3[3];
-                cross(wh, exa, Wexa);
-                cross(Jq, ua, c1v);                                  // [J_q e_i x] (alpha_arg a), NEW J_q
-                cross(Jq, ub, c2v);
-                const double wi = wh[0];
+                const double be = FST(FS_BE);
+                FST(FS_AL) = FST(FS_AL) + be * dt + (R1[0] * ua[0] + R1[3] * ua[1] + R1[6] * ua[2]);
+                FST(FS_BE) = be + (R1[0] * ub[0] + R1[3] * ub[1] + R1[6] * ub[2]);
+            }
+
+            if (MODEL == 1) {
+                // ---- analytic bias Jacobians, own column (CpiV1.h:162-259)
+                const double d1 = scj[SC_D1], d2 = scj[SC_D2], d3 = scj[SC_D3], d4 = scj[SC_D4], ca = scj[SC_CA], cb = scj[SC_CB];
+                // [w x] and [w x]^2, column 0:  W[:,0] = (0, w2, -w1),  W2[:,0] = (-(w1^2 + w2^2), w0 w1, w0 w2)
+                const double Wc[3] = {0.0, wh[2], -wh[1]};
+                const double W2c[3] = {-(wh[1] * wh[1] + wh[2] * wh[2]), wh[0] * wh[1], wh[0] * wh[2]};
+                double aargc[3], bargc[3], Hal[3], Hbe[3], Jq[3], Ja[3], Jb[3], Ha[3], Hb[3];
+#pragma unroll
+                for (int e = 0; e < 3; e++) { Jq[e] = FST(FS_JQ + e); Ja[e] = FST(FS_JA + e); Jb[e] = FST(FS_JB + e); Ha[e] = FST(FS_HA + e); Hb[e] = FST(FS_HB + e); }
 #pragma unroll
                 for (int e = 0; e < 3; e++) {
-                    va_[e] = -c1v[e] + (wi * d1) * Wa[e] - f1 * exa[e] + (wi * d2) * W2a[e] - f2 * (exWa[e] + Wexa[e]);
-                    vb_[e] = -c2v[e] + (wi * d3) * Wa[e] - f3 * exa[e] + (wi * d4) * W2a[e] - f4 * (exWa[e] + Wexa[e]);
+                    aargc[e] = ((e == 0) ? hdt2 : 0.0) + f1 * Wc[e] + f2 * W2c[e];
+                    bargc[e] = ((e == 0) ? dt : 0.0) + f3 * Wc[e] + f4 * W2c[e];
                 }
-                mvT33(R1, va_, oa3);
-                mvT33(R1, vb_, ob3);
+                mvT33(R1, aargc, Hal);                               // column of R_tau12k * alpha_arg
+                mvT33(R1, bargc, Hbe);
+                {
+                    double t3[3];
+                    rot_col(a1, b1, wh, Jq, t3);                     // R_tau2tau1 * J_q
 #pragma unroll
-                for (int r = 0; r < 3; r++) {                        // J_a += J_b dt (old J_b, CpiV1.h:241) then the column terms
-                    FST(FS_JA + r) = (Ja[r] + Jb[r] * dt) + oa3[r];
-                    FST(FS_JB + r) = Jb[r] + ob3[r];
+                    for (int e = 0; e < 3; e++) { Jq[e] = t3[e] + (((e == 0) ? 1.0 : 0.0) - ca * Wc[e] + cb * W2c[e]) * dt; FST(FS_JQ + e) = Jq[e]; }   // CpiV1.h:167
+                }
+#pragma unroll
+                for (int e = 0; e < 3; e++) {                        // CpiV1.h:170-172 (old H_b)
+                    FST(FS_HA + e) = (Ha[e] - Hal[e]) + dt * Hb[e];
+                    FST(FS_HB + e) = Hb[e] - Hbe[e];
+                }
+                {
+                    // column 0 of the frame: e_0 x a = (0, -a2, a1)
+                    const double exa[3] = {0.0, -ah[2], ah[1]}, exWa[3] = {0.0, -Wa[2], Wa[1]};
+                    double Wexa[3], c1v[3], c2v[3], va_[3], vb_[3], oa3[3], ob3[3];
+                    cross(wh, exa, Wexa);
+                    cross(Jq, ua, c1v);                              // [J_q e_i x] (alpha_arg a), NEW J_q
+                    cross(Jq, ub, c2v);
+                    const double wi = wh[0];
+#pragma unroll
+                    for (int e = 0; e < 3; e++) {
+                        va_[e] = -c1v[e] + (wi * d1) * Wa[e] - f1 * exa[e] + (wi * d2) * W2a[e] - f2 * (exWa[e] + Wexa[e]);
+                        vb_[e] = -c2v[e] + (wi * d3) * Wa[e] - f3 * exa[e] + (wi * d4) * W2a[e] - f4 * (exWa[e] + Wexa[e]);
+                    }
+                    mvT33(R1, va_, oa3);
+                    mvT33(R1, vb_, ob3);
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {                    // J_a += J_b dt (old J_b, CpiV1.h:241) then the column terms
+                        FST(FS_JA + r) = (Ja[r] + Jb[r] * dt) + oa3[r];
+                        FST(FS_JB + r) = Jb[r] + ob3[r];
+                    }
                 }
             }
-        }
-        if (MODEL == 2) {
-            // ---- Discrete_J_b <- B_k Phi Discrete_J_b on the consumed columns (CpiV2.h:347-426, 443).  Phi is RK4 on Phi' = F Phi, a
-            // LINEAR map, so it is applied directly to this lane's own columns (bg_c, ba_c, l_c) of Discrete_J_b: same four stages,
-            // no Phi ever formed, nothing crosses lanes.  Rows: theta' = -W theta - e_c (bg column only); v' = A_s theta + C_s theta(start)
-            // (the clone rows equal the theta rows at the start of every step, B_k) + B_s e_c (ba column) + L_s e_c (l column); p' = v.
-            const double hdt = 0.5 * dt, dt6 = dt / 6.0;
-            double xt[3], xv[3], st[3], sv[3], sp[3], gxt0[3];
-            const double Dtg[3] = {FST(FS_DTG), FST(FS_DTG + 1), FST(FS_DTG + 2)}, Dvg[3] = {FST(FS_DVG), FST(FS_DVG + 1), FST(FS_DVG + 2)};
-            cross(g_tau, Dtg, gxt0);                                 // g_tau x theta(start): the C_s term is -R_s^T of this
+            if (MODEL == 2) {
+                // ---- Discrete_J_b <- B_k Phi Discrete_J_b on the consumed columns (CpiV2.h:347-426, 443).  Phi is RK4 on Phi' = F Phi, a
+                // LINEAR map, so it is applied directly to this lane's own columns (bg_c, ba_c, l_c) of Discrete_J_b: same four stages,
+                // no Phi ever formed, nothing crosses lanes.  Rows: theta' = -W theta - e_c (bg column only); v' = A_s theta + C_s theta(start)
+                // (the clone rows equal the theta rows at the start of every step, B_k) + B_s e_c (ba column) + L_s e_c (l column); p' = v.
+                const double hdt = 0.5 * dt, dt6 = dt / 6.0;
+                double xt[3], xv[3], st[3], sv[3], sp_[3], gxt0[3];
+                const double Dtg[3] = {FST(FS_DTG), FST(FS_DTG + 1), FST(FS_DTG + 2)}, Dvg[3] = {FST(FS_DVG), FST(FS_DVG + 1), FST(FS_DVG + 2)};
+                cross(g_tau, Dtg, gxt0);                             // g_tau x theta(start): the C_s term is -R_s^T of this
 #pragma unroll
-            for (int e = 0; e < 3; e++) { xt[e] = Dtg[e]; xv[e] = Dvg[e]; }
+                for (int e = 0; e < 3; e++) { xt[e] = Dtg[e]; xv[e] = Dvg[e]; }
 #pragma unroll
-            for (int s = 0; s < 4; s++) {
-                const double* Rs = (s == 0) ? R : (s == 3 ? R1 : Rm);
-                const double cn = (s < 2) ? hdt : dt;
-                double kt[3], u[3], kv[3];
-                cross(xt, wh, kt);
-                kt[0] -= 1.0;
-                cross(ah, xt, u);
+                for (int s = 0; s < 4; s++) {
+                    const double* Rs = (s == 0) ? R : (s == 3 ? R1 : Rm);
+                    const double cn = (s < 2) ? hdt : dt;
+                    double kt[3], u[3], kv[3];
+                    cross(xt, wh, kt);
+                    kt[0] -= 1.0;
+                    cross(ah, xt, u);
 #pragma unroll
-                for (int e = 0; e < 3; e++) u[e] += gxt0[e];
-                negRt(Rs, u, kv);
+                    for (int e = 0; e < 3; e++) u[e] += gxt0[e];
+                    negRt(Rs, u, kv);
+#pragma unroll
+                    for (int e = 0; e < 3; e++) {
+                        st[e] = (s == 0) ? kt[e] : (s == 3 ? st[e] + kt[e] : st[e] + 2.0 * kt[e]);
+                        sv[e] = (s == 0) ? kv[e] : (s == 3 ? sv[e] + kv[e] : sv[e] + 2.0 * kv[e]);
+                        sp_[e] = (s == 0) ? xv[e] : (s == 3 ? sp_[e] + xv[e] : sp_[e] + 2.0 * xv[e]);
+                        if (s < 3) { xt[e] = Dtg[e] + cn * kt[e]; xv[e] = Dvg[e] + cn * kv[e]; }
+                    }
+                }
 #pragma unroll
                 for (int e = 0; e < 3; e++) {
-                    st[e] = (s == 0) ? kt[e] : (s == 3 ? st[e] + kt[e] : st[e] + 2.0 * kt[e]);
-                    sv[e] = (s == 0) ? kv[e] : (s == 3 ? sv[e] + kv[e] : sv[e] + 2.0 * kv[e]);
-                    sp[e] = (s == 0) ? xv[e] : (s == 3 ? sp[e] + xv[e] : sp[e] + 2.0 * xv[e]);
-                    if (s < 3) { xt[e] = Dtg[e] + cn * kt[e]; xv[e] = Dvg[e] + cn * kv[e]; }
+                    FST(FS_DTG + e) = Dtg[e] + dt6 * st[e];
+                    FST(FS_DVG + e) = Dvg[e] + dt6 * sv[e];
+                    FST(FS_DPG + e) = FST(FS_DPG + e) + dt6 * sp_[e];
+                }
+                // ba and l columns: v' = B_s e_c = -(row 0 of R_s),  v' = L_s e_c = -R_s^T (R_old [g_k x] e_c)  (CpiV2.h:336); p' = v
+                const double gk[3] = {FST(FS_GK), FST(FS_GK + 1), FST(FS_GK + 2)};
+                const double sk0[3] = {0.0, gk[2], -gk[1]};          // [g_k x] e_0
+                double y[3], l0[3], lm[3], l1[3];
+                mv33(R, sk0, y);
+                negRt(R, y, l0); negRt(Rm, y, lm); negRt(R1, y, l1);
+                const double Ppv = dt6 * (1.0 + 2.0 + 2.0 + 1.0);
+#pragma unroll
+                for (int e = 0; e < 3; e++) {
+                    const double b0 = -R[e], bm = -Rm[e], b1_ = -R1[e];
+                    const double dva = FST(FS_DVA + e), dvl = FST(FS_DVL + e);
+                    FST(FS_DPA + e) = dt6 * (2.0 * (b0 * hdt) + 2.0 * (bm * hdt) + bm * dt) + Ppv * dva + FST(FS_DPA + e);
+                    FST(FS_DVA + e) = dt6 * (b0 + 2.0 * bm + 2.0 * bm + b1_) + dva;
+                    FST(FS_DPL + e) = dt6 * (2.0 * (l0[e] * hdt) + 2.0 * (lm[e] * hdt) + lm[e] * dt) + Ppv * dvl + FST(FS_DPL + e);
+                    FST(FS_DVL + e) = dt6 * (l0[e] + 2.0 * lm[e] + 2.0 * lm[e] + l1[e]) + dvl;
                 }
             }
-#pragma unroll
-            for (int e = 0; e < 3; e++) {
-                FST(FS_DTG + e) = Dtg[e] + dt6 * st[e];
-                FST(FS_DVG + e) = Dvg[e] + dt6 * sv[e];
-                FST(FS_DPG + e) = FST(FS_DPG + e) + dt6 * sp[e];
-            }
-            // ba and l columns: v' = B_s e_c = -(row 0 of R_s),  v' = L_s e_c = -R_s^T (R_old [g_k x] e_c)  (CpiV2.h:336); p' = v
-            const double gk[3] = {FST(FS_GK), FST(FS_GK + 1), FST(FS_GK + 2)};
-            const double sk0[3] = {0.0, gk[2], -gk[1]};              // [g_k x] e_0
-            double y[3], l0[3], lm[3], l1[3];
-            mv33(R, sk0, y);
-            negRt(R, y, l0); negRt(Rm, y, lm); negRt(R1, y, l1);
-            const double Ppv = dt6 * (1.0 + 2.0 + 2.0 + 1.0);
-#pragma unroll
-            for (int e = 0; e < 3; e++) {
-                const double b0 = -R[e], bm = -Rm[e], b1 = -R1[e];
-                const double dva = FST(FS_DVA + e), dvl = FST(FS_DVL + e);
-                FST(FS_DPA + e) = dt6 * (2.0 * (b0 * hdt) + 2.0 * (bm * hdt) + bm * dt) + Ppv * dva + FST(FS_DPA + e);
-                FST(FS_DVA + e) = dt6 * (b0 + 2.0 * bm + 2.0 * bm + b1) + dva;
-                FST(FS_DPL + e) = dt6 * (2.0 * (l0[e] * hdt) + 2.0 * (lm[e] * hdt) + lm[e] * dt) + Ppv * dvl + FST(FS_DPL + e);
-                FST(FS_DVL + e) = dt6 * (l0[e] + 2.0 * lm[e] + 2.0 * lm[e] + l1[e]) + dvl;
-            }
-        }
-        CPI_FENCE();
+            CPI_FENCE();
 
-        // ---- covariance RK4 (CpiV1.h:272-353)
-        {
-            T w_[3], a_[3], g_[3], R_[9], Rm_[9], R1_[9];
+            // ---- covariance RK4 (CpiV1.h:272-353)
+            {
+                T w_[3], a_[3], g_[3], R_[9], Rm_[9], R1_[9];
 #pragma unroll
-            for (int e = 0; e < 3; e++) { w_[e] = (T)wh[e]; a_[e] = (T)ah[e]; g_[e] = (T)g_tau[e]; }
+                for (int e = 0; e < 3; e++) { w_[e] = (T)wh[e]; a_[e] = (T)ah[e]; g_[e] = (T)g_tau[e]; }
 #pragma unroll
-            for (int e = 0; e < 9; e++) { R_[e] = (T)R[e]; Rm_[e] = (T)Rm[e]; R1_[e] = (T)R1[e]; }
-            const double dt6 = dt / 6.0;
-            tri_cov_step<MODEL, T>(P, sl, w_, a_, g_, R_, Rm_, R1_, (T)pgg, (T)paa, (T)dt, (T)dt6, (T)p.q_w, (T)p.q_wb, (T)p.q_a, (T)p.q_ab, nx, pv);
-            pgg += dt6 * (p.q_wb + 2.0 * p.q_wb + 2.0 * p.q_wb + p.q_wb);
-            paa += dt6 * (p.q_ab + 2.0 * p.q_ab + 2.0 * p.q_ab + p.q_ab);
+                for (int e = 0; e < 9; e++) { R_[e] = (T)R[e]; Rm_[e] = (T)Rm[e]; R1_[e] = (T)R1[e]; }
+                const double dt6 = dt / 6.0;
+                tri_cov_step<MODEL, NT, T>(P, sl, w_, a_, g_, R_, Rm_, R1_, (T)pgg, (T)paa, (T)dt, (T)dt6, (T)p.q_w, (T)p.q_wb, (T)p.q_a, (T)p.q_ab, nx, pv);
+                pgg += dt6 * (p.q_wb + 2.0 * p.q_wb + 2.0 * p.q_wb + p.q_wb);
+                paa += dt6 * (p.q_ab + 2.0 * p.q_ab + 2.0 * p.q_ab + p.q_ab);
+            }
+#pragma unroll
+            for (int e = 0; e < 9; e++) R[e] = R1[e];                // CpiV1.h:357
         }
-#pragma unroll
-        for (int e = 0; e < 9; e++) R[e] = R1[e];                    // CpiV1.h:357
+        __syncwarp();                                                // all lanes are done with this group's scalar sets and staged samples
+        // ---- refill: every chunk whose samples all lie before it0 + 3 has been consumed by the three lanes
+        if (c == 0 && next_issue < n_tma) {
+            const int consumed = (it0 + 3) / CH;
+            while (next_issue < n_tma && next_issue - TRI_NBUF < consumed) {
+                const int b = next_issue % TRI_NBUF;
+                fence_proxy_async();
+                mbar_arrive_expect_tx(bar0 + 8 * b, 128);
+                bulk_g2s(buf0 + 128 * b, sp + 7 * CH * next_issue - shift, 128, bar0 + 8 * b);
+                next_issue++;
+            }
+        }
     }
 
     // ---- write the record (column-major 3x3 / 15x15, include/cpi_b200.h).  Lane c writes original column c (rows c, c+1, c+2).
@@ -650,13 +716,17 @@ static cudaError_t launch_tri_one(const PreintParams& p0, int num_sms, cudaStrea
     }
     // windows per block: one wave over all SMs if the batch fits (latency-bound regime), else the CTA capacity
     const int64_t need = (p.n_windows + num_sms - 1) / num_sms;
-    if (p.wpb <= 0 || p.wpb > TRI_WPB) p.wpb = (int)(need <= TRI_WPB ? (need < 1 ? 1 : need) : TRI_WPB);
+    constexpr int WPB = TriSmem<MODEL, T>::WPB;
+    if (p.wpb <= 0 || p.wpb > WPB) p.wpb = (int)(need <= WPB ? (need < 1 ? 1 : need) : WPB);
     const int grid = (int)((p.n_windows + p.wpb - 1) / p.wpb);
-    kern<<<grid, TRI_THREADS, smem, st>>>(p);
+    kern<<<grid, TriSmem<MODEL, T>::NT, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-int preint_tri_cap() { return TRI_WPB; }
+int preint_tri_cap(int model, int dtype) {
+    if (model == 1) return dtype == 32 ? TriSmem<1, float>::WPB : TriSmem<1, double>::WPB;
+    return dtype == 32 ? TriSmem<2, float>::WPB : TriSmem<2, double>::WPB;
+}
 bool preint_tri_supported(int model, int flags) {
     if (flags & CPI_FLAG_IMU_AVG) return false;
     return model == 1 || (model == 2 && !(flags & CPI_FLAG_ANALYTIC_JACOBIANS));

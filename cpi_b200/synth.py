@@ -41,26 +41,42 @@ def _rot_step(w, dt):
     return eye - a[:, None, None] * k + b[:, None, None] * (k @ k)
 
 
-def _block(seed, block, nb, ns, rate, special, entries):
+def _draw(seed, block, nb, entries):
+    """All random draws of one block, in a fixed order, from the block's own Philox stream."""
     g = np.random.Generator(np.random.Philox(key=[seed, block]))
-    dt0 = 1.0 / rate
-    w0 = g.uniform(-1, 1, (nb, 3)); Aw = g.uniform(0, 1.5, (nb, 3)); fw = g.uniform(0.2, 2, (nb, 3)); pw = g.uniform(0, 2 * np.pi, (nb, 3))
-    Aa = g.uniform(0, 2, (nb, 3)); fa = g.uniform(0.2, 2, (nb, 3)); pa = g.uniform(0, 2 * np.pi, (nb, 3))
-    b_w = g.normal(0, 1e-3, (nb, 3)); b_a = g.normal(0, 1e-2, (nb, 3))
+    d = {}
+    d["w0"] = g.uniform(-1, 1, (nb, 3)); d["Aw"] = g.uniform(0, 1.5, (nb, 3)); d["fw"] = g.uniform(0.2, 2, (nb, 3)); d["pw"] = g.uniform(0, 2 * np.pi, (nb, 3))
+    d["Aa"] = g.uniform(0, 2, (nb, 3)); d["fa"] = g.uniform(0.2, 2, (nb, 3)); d["pa"] = g.uniform(0, 2 * np.pi, (nb, 3))
+    d["b_w"] = g.normal(0, 1e-3, (nb, 3)); d["b_a"] = g.normal(0, 1e-2, (nb, 3))
     q = g.normal(0, 1, (nb, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True); q[q[:, 3] < 0] *= -1
-    lin = np.concatenate([b_w, b_a, q, np.broadcast_to(GRAVITY, (nb, 3))], axis=1)
-    dts = np.where(g.uniform(size=(nb, entries)) < 0.05, 2 * dt0, dt0)
-    nz_w = g.normal(size=(nb, entries, 3)); nz_a = g.normal(size=(nb, entries, 3))
-    rw_w = g.normal(size=(nb, entries, 3)); rw_a = g.normal(size=(nb, entries, 3))
-    kind = g.uniform(size=nb)
-    scale = g.uniform(1e-4, 0.008, size=(nb, entries))
-    zpos = g.integers(0, max(entries, 1), size=nb)
+    d["q"] = q
+    d["dsel"] = g.uniform(size=(nb, entries))
+    d["nz_w"] = g.normal(size=(nb, entries, 3)); d["nz_a"] = g.normal(size=(nb, entries, 3))
+    d["rw_w"] = g.normal(size=(nb, entries, 3)); d["rw_a"] = g.normal(size=(nb, entries, 3))
+    d["kind"] = g.uniform(size=nb)
+    d["scale"] = g.uniform(1e-4, 0.008, size=(nb, entries))
+    d["zpos"] = g.integers(0, max(entries, 1), size=nb)
+    d["bw_off"] = g.normal(0, 1e-4, (nb, 3)); d["ba_off"] = g.normal(0, 1e-3, (nb, 3))
+    return d
 
-    S = np.zeros((nb, entries, 7))
-    R = np.broadcast_to(np.eye(3), (nb, 3, 3)).copy()
-    t = np.zeros(nb)
-    bw = b_w + g.normal(0, 1e-4, (nb, 3))      # true bias near (not at) the linearisation point
-    ba = b_a + g.normal(0, 1e-3, (nb, 3))
+
+def _blocks(seed, blocks, nb, ns, rate, special, entries):
+    """Windows of several blocks at once: the draws come from each block's own stream, the time loop runs over all of them
+    together (every operation is per window, so the result does not depend on how blocks are grouped)."""
+    ds = [_draw(seed, b, nb, entries) for b in blocks]
+    D = {k: np.concatenate([d[k] for d in ds]) for k in ds[0]}
+    n = nb * len(blocks)
+    dt0 = 1.0 / rate
+    w0, Aw, fw, pw, Aa, fa, pa, b_w, b_a = (D[k] for k in ("w0", "Aw", "fw", "pw", "Aa", "fa", "pa", "b_w", "b_a"))
+    lin = np.concatenate([b_w, b_a, D["q"], np.broadcast_to(GRAVITY, (n, 3))], axis=1)
+    dts = np.where(D["dsel"] < 0.05, 2 * dt0, dt0)
+    nz_w, nz_a, rw_w, rw_a, kind, scale, zpos = (D[k] for k in ("nz_w", "nz_a", "rw_w", "rw_a", "kind", "scale", "zpos"))
+
+    S = np.zeros((n, entries, 7))
+    R = np.broadcast_to(np.eye(3), (n, 3, 3)).copy()
+    t = np.zeros(n)
+    bw = b_w + D["bw_off"]                     # true bias near (not at) the linearisation point
+    ba = b_a + D["ba_off"]
     for i in range(entries):
         dt = dts[:, i]
         w = w0 + Aw * np.sin(2 * np.pi * fw * t[:, None] + pw)
@@ -94,16 +110,50 @@ def _block(seed, block, nb, ns, rate, special, entries):
     return S, lin
 
 
+def usable_cpus():
+    """Host threads this process may actually use: scheduler affinity capped by the cgroup CPU quota (v2 cpu.max or v1 cfs)."""
+    import math
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, math.ceil(int(quota) / int(period))))
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, math.ceil(q / per)))
+        except (OSError, ValueError):
+            pass
+    return max(1, n)
+
+
 def make_windows(n_windows, ns, rate=200.0, seed=SEED, first_window=0, special=True, imu_avg=False):
     """Return (samples[n, entries, 7], lin[n, 13]) for windows first_window .. first_window+n_windows-1.
 
-    entries = ns (+1 trailing entry if imu_avg).  Deterministic in (seed, absolute window index, ns, rate).
+    entries = ns (+1 trailing entry if imu_avg).  Deterministic in (seed, absolute window index, ns, rate).  Blocks are
+    independent Philox streams; groups of 4 blocks share one pass of the per-sample time loop, groups run on a thread pool.
     """
     entries = ns + (1 if imu_avg else 0)
     b0, b1 = first_window // BLOCK, (first_window + n_windows + BLOCK - 1) // BLOCK
     Ss, Ls = [], []
-    for b in range(b0, b1):
-        S, L = _block(seed, b, BLOCK, ns, rate, special, entries)
+    groups = [list(range(g0, min(g0 + 4, b1))) for g0 in range(b0, b1, 4)]
+    gen = lambda grp: _blocks(seed, grp, BLOCK, ns, rate, special, entries)
+    nthr = min(usable_cpus(), 16, len(groups))
+    if nthr > 1:                                  # numpy releases the GIL on these array sizes
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(nthr) as ex:
+            outs = list(ex.map(gen, groups))
+    else:
+        outs = [gen(g) for g in groups]
+    blocks = []
+    for grp, (Sg, Lg) in zip(groups, outs):
+        blocks += [(Sg[i * BLOCK:(i + 1) * BLOCK], Lg[i * BLOCK:(i + 1) * BLOCK]) for i in range(len(grp))]
+    for b, (S, L) in zip(range(b0, b1), blocks):
         lo = max(first_window - b * BLOCK, 0)
         hi = min(first_window + n_windows - b * BLOCK, BLOCK)
         Ss.append(S[lo:hi]); Ls.append(L[lo:hi])

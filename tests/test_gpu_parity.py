@@ -12,6 +12,10 @@ from parity import compare_records, window_band
 pytestmark = pytest.mark.gpu
 CASES = ("cam200", "real200", "real100", "real400", "synth200", "edge")
 MODES = [(1, 0), (1, 1), (2, 0), (2, 1), (2, 2), (2, 3)]
+# fp32-storage variant (dtype 32): no fp32 reference exists; gates = 2x the worst error observed on B200 against the fp64 oracle on the
+# same float-rounded inputs.  R/alpha/beta/J/H: fp64 arithmetic, float output rounding; P: fp32 RK4.
+FP32_GATES = {1: dict(R=2e-7, alpha=2e-7, beta=2e-7, J_q=2e-7, J_a=2e-7, J_b=2e-7, H_a=2e-7, H_b=2e-7, P=2e-4, P_block=2e-4),
+              2: dict(R=2e-7, alpha=2e-7, beta=2e-7, J_q=5e-6, J_a=5e-6, J_b=5e-6, H_a=5e-6, H_b=5e-6, O_a=5e-6, O_b=5e-6, P=2e-4, P_block=2e-4)}
 
 
 def _inputs(G, name, flags):
@@ -307,3 +311,46 @@ def test_sharded_entry_point_on_device(cuda):
     got = shard.preintegrate_sharded(2, S.reshape(-1, 7), L, synth.SIGMAS, 0, ns=40)
     cuda.cuda.synchronize()
     assert np.array_equal(got.cpu().numpy(), preint.preintegrate_host(2, S, L, synth.SIGMAS, 0, ns=40))
+
+
+def _sample_of_windows(n, cap, S, L):
+    """First CTA, a CTA in the middle, the last full CTA, the last partial CTA, a stride through the batch, every forced special
+    window (small_w / zero w_hat / dt = 0)."""
+    mag = np.linalg.norm(S[:, :, 0:3].astype(np.float64) - L[:, None, 0:3].astype(np.float64), axis=2)
+    special = np.where((mag.max(axis=1) < 0.0088) | (S[:, :, 6].min(axis=1) == 0))[0][:40]
+    last_full = (n // cap - 1) * cap
+    mid = (n // cap // 2) * cap
+    return np.unique(np.r_[0:cap, mid:mid + cap, last_full:last_full + cap, (n // cap) * cap:n, np.arange(0, n, 401), special]).astype(np.int64)
+
+
+@pytest.mark.parametrize("model,dtype,n,ns", [(1, np.float64, 25003, 200), (1, np.float32, 25003, 200), (2, np.float64, 12037, 400), (2, np.float32, 12037, 400)])
+def test_multiwave_capacity_path(cuda, oracle, model, dtype, n, ns):
+    """Batches of several waves of full-capacity CTAs (25k x 200 model 1 = 313 CTAs of 80 windows; 12k x 400 model 2): the
+    grid-sizing path BASELINE configs[2] / configs[3] run, compared window by window with the compiled reference (oracle/_ref; the C
+    port where it did not travel) on the first / a middle / the last full / the last partial CTA, a stride and all special windows."""
+    from cpi_b200 import preint
+    from oracle import oracle as om
+    from parity import fp32_errors
+    torch = cuda
+    ref_impl = om.Reference() if om.Reference.available() else oracle
+    rate = 200.0 if ns == 200 else 400.0
+    S, L = synth.make_windows(n, ns, rate=rate, first_window=50000)
+    Sx, Lx = S.astype(dtype), L.astype(dtype)
+    got = preint.preintegrate(model, torch.from_numpy(Sx).cuda(), torch.from_numpy(Lx).cuda(), synth.SIGMAS, 0, ns=ns)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    assert np.all(np.isfinite(got))
+    cap = 80 if not (model == 2 and dtype == np.float64) else 60
+    sel = _sample_of_windows(n, cap, Sx, Lx)
+    ref = ref_impl.preintegrate(model, Sx[sel].astype(np.float64), Lx[sel].astype(np.float64), synth.SIGMAS, 0, ns=ns, nthreads=16)
+    if dtype == np.float64:
+        off = np.arange(len(sel) + 1, dtype=np.int64) * ns
+        worst = compare_records(got[sel], ref, model, in_band=window_band(S[sel].reshape(-1, 7), off, L[sel]))
+    else:
+        worst = fp32_errors(got[sel], ref)
+        for k, gate in FP32_GATES[model].items():
+            assert worst[k] <= gate, (k, worst[k], gate)
+    print(model, dtype.__name__, n, ns, len(sel), {k: f"{v:.1e}" for k, v in worst.items()})
+    # host entry point (chunk-pipelined) gives the same bits
+    host = preint.preintegrate_host(model, Sx, Lx, synth.SIGMAS, 0, ns=ns)
+    assert np.array_equal(host, got)
