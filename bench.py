@@ -7,9 +7,13 @@ One "step" = one pass of the hot path over one batch of synthetic IMU windows (c
 Default workload = BASELINE.json configs[1]: 10 000 windows x 200 samples, CPI model 1 (mean + Jacobians + covariance),
 fp64, per GPU.  With N > 1 every rank preintegrates its own 10k-window shard (weak scaling, windows are independent) and
 the step ends with ONE NCCL all-gather of the result records, the kernel having written its shard straight into its
-slice of the gather buffer.  Timing: W untimed warm-up steps, then K steps between barrier + synchronize, CUDA events on
+slice of the gather buffer -- both through the product's C ABI (cpi_preintegrate_batch_sharded, cpi_b200.shard.Communicator):
+the all-gather runs on the communicator's own stream, so step i's collective overlaps step i+1's kernel (two gather buffers).  Timing: W untimed warm-up steps, then K steps between barrier + synchronize, CUDA events on
 the launching stream, max over ranks.  Inputs rotate over several distinct resident batches whose total size exceeds
 the 126 MB L2, so no step finds its samples in cache.
+
+The default run appends a "configs" array to the same JSON line: short measurements of the other BASELINE configs
+(configs[2] v2 100k x 400, configs[3] fp32 125k per GPU, configs[4] the 5k factor chain, configs[0] single window).
 
 Extra keys: roofline (dominant kernel vs the measured fp64 DFMA peak and vs measured HBM bandwidth), cpu_baseline (the
 reference's own CPU implementation timed on this box's host cores, rank 0, N = 1), e2e (same metric through the C-ABI
@@ -51,8 +55,9 @@ WORKLOADS = {
 }
 FFMA_PEAK_TFLOPS = 72.51   # same microbenchmark, fp32 FFMA
 DFMA_PEAK_TFLOPS = 34.17   # measured on this pool's B200 by tools/microbench.cu (profiles/microbench_r01.jsonl), burst == sustained
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/*.txt)
-NCU_TRAFFIC_BYTES = {"v1_10k_200": 113.78e6 + 3.72e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the CURRENT kernels
+# (profiles/r02_*.txt); None where no capture exists
+NCU_TRAFFIC = {"v1_10k_200": (114.05e6 + 4.16e6, "profiles/r02_k1_tri_v1_prepass.txt")}
 
 
 def measured_peaks():
@@ -114,7 +119,7 @@ def cpu_arm(wl, sample_windows, nthreads=None):
         if not os.path.exists(Oracle.path):
             subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "liboracle.so"], check=True)
         impl, kind = Oracle(), "port"
-    cores = nthreads or os.cpu_count() or 1
+    cores = nthreads or synth.usable_cpus()        # scheduler affinity capped by the cgroup quota: the threads we can actually run
     S, L = synth.make_windows(sample_windows, wl["ns"], rate=wl["rate"])
     impl.preintegrate(wl["model"], S[:cores], L[:cores], synth.SIGMAS, 0, ns=wl["ns"], nthreads=cores)   # warm
     t0 = time.perf_counter()
@@ -123,15 +128,30 @@ def cpu_arm(wl, sample_windows, nthreads=None):
     return sample_windows / dt, kind, cores, dt
 
 
+def config_dict(wl, world, note=None):
+    """The SAME dict on both arms (the driver compares them): the workload, not how an arm samples it."""
+    n, ns, model = wl["n"], wl["ns"], wl["model"]
+    f32 = bool(wl.get("fp32"))
+    es = 4 if f32 else 8
+    if wl.get("factor"):
+        return {"workload": wl["desc"], "factors_per_step": n, "model": f"ImuFactorCPIv{model}", "parallelism": "rank 0 only (the solver lives there)",
+                "l2": "192 MB buffer written between timed launches (outside the event pair)"}
+    bytes_in = n * ns * 7 * es + n * 13 * es
+    nb = 2 if bytes_in > 300e6 else min(8, max(2, int(np.ceil(300e6 / bytes_in))))
+    return {"workload": wl["desc"], "windows_per_gpu": n, "samples_per_window": ns, "model": f"CpiV{model}",
+            "parallelism": f"window-sharded x{world}" + (", one NCCL all-gather of records per step (overlapped with the next step's kernel)" if world > 1 else ""),
+            "l2": f"{nb} rotating resident input batches = {nb * bytes_in / 1e6:.0f} MB > 126 MB L2"}
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    from cpi_b200 import synth
+    cores = synth.usable_cpus()
     if wl.get("single"):
         # SURVEY 8(d) config 1: one window, reference CpiV1 on ONE thread, median of >= 1000 repeats
         from oracle.oracle import Oracle, Reference
-        from cpi_b200 import synth
         impl, kind = (Reference(), "reference") if Reference.available() else (Oracle(), "port")
         S, L = synth.make_windows(1, wl["ns"], rate=wl["rate"], special=False)
         ts = []
@@ -140,11 +160,11 @@ def run_reference(args, wl):
         ms = 1e3 * float(np.median(ts[200:]))
         print(json.dumps({"impl": "reference", "metric": "imu_windows_per_sec", "value": 1e3 / ms, "unit": "windows/s", "n_gpus": args.gpus, "steps": 1000, "warmup": 200,
                           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": wl["desc"], "windows_per_step": 1, "samples_per_window": wl["ns"], "model": "CpiV1"},
+                          "config": config_dict(wl, args.gpus),
                           "cpu_baseline": {"value": 1e3 / ms, "unit": "windows/s", "cores": 1, "kind": kind, "sample": "1 window x 100 samples, median of 1000 repeats (includes ~3 us of ctypes call overhead)"},
                           "e2e": {"value": 1e3 / ms, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
         return
-    # bounded sample: calibrate on a small run, then size each step for ~5 s of CPU work (all host threads)
+    # bounded sample: calibrate on a small run, then size each step for ~5 s of CPU work (all usable host threads)
     v0, kind, cores, _ = cpu_arm(wl, max(2 * cores, 64))
     sample = int(min(wl["n"], max(cores, v0 * 5.0)))
     times = []
@@ -155,15 +175,17 @@ def run_reference(args, wl):
     ms = 1e3 * float(np.mean(times))
     value = sample / (ms * 1e-3)
     line = {"impl": "reference", "metric": "imu_windows_per_sec", "value": value, "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": wl["desc"], "windows_per_step": sample, "samples_per_window": wl["ns"], "model": f"CpiV{wl['model']}"},
-            "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": kind,
-                             "sample": f"{sample} windows x {wl['ns']} samples per step, {'oracle/_ref (unmodified reference, std::thread over windows)' if kind == 'reference' else 'oracle C port'}"},
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 storage + f32 covariance RK4, f64 rotations/coefficients/means" if wl.get("fp32") else "f64",
+            "data": "synthetic", "config": config_dict(wl, args.gpus),
+            "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "cores_online": os.cpu_count(), "kind": kind,
+                             "sample": f"{sample} windows x {wl['ns']} samples per step, {'oracle/_ref (unmodified reference, std::thread over windows)' if kind == 'reference' else 'oracle C port'}"
+                                       + (" -- the reference is double-only: the fp64 path on the same inputs" if wl.get("fp32") else "")},
             "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def run_factor(args, wl):
+def run_factor(args, wl, emit=True, cpu=True):
     """configs[4]: K3 (ImuFactorCPIv1::evaluateError batched) over a 5k-keyframe chain.  HBM-write bound: 4 496 algorithmic
     bytes per factor (776 in, 3 720 out); at 5k factors the launch is ~10 us, i.e. launch-latency sized."""
     from cpi_b200 import synth
@@ -174,7 +196,7 @@ def run_factor(args, wl):
         if int(os.environ.get("RANK", "0")) != 0:
             return
         impl, kind = (Reference(), "reference") if Reference.available() else (Oracle(), "port")
-        cores = os.cpu_count() or 1
+        cores = synth.usable_cpus()
         rec = impl.preintegrate(model, S, L, synth.SIGMAS, 0, ns=ns, nthreads=cores)
         X = synth.make_states(rec, L, model)
         ts = []
@@ -183,12 +205,11 @@ def run_factor(args, wl):
         ms = 1e3 * float(np.mean(ts[args.warmup:])); v = n / (ms * 1e-3)
         print(json.dumps({"impl": "reference", "metric": "imu_factors_per_sec", "value": v, "unit": "factors/s", "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": wl["desc"]}, "cpu_baseline": {"value": v, "unit": "factors/s", "cores": cores, "kind": kind, "sample": f"{n} factors per step"},
+                          "config": config_dict(wl, args.gpus), "cpu_baseline": {"value": v, "unit": "factors/s", "cores": cores, "kind": kind, "sample": f"{n} factors per step"},
                           "e2e": {"value": v, "unit": "factors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
         return
     import torch
     from cpi_b200 import capi, factor, preint
-    torch.cuda.set_device(0)
     lib = capi.load()
     rec = preint.preintegrate_host(model, S, L, synth.SIGMAS, 0, ns=ns)
     X = synth.make_states(rec, L, model)
@@ -227,21 +248,264 @@ def run_factor(args, wl):
     e2e_ms = (time.perf_counter() - t0) * 100.0
     out = {"metric": "imu_factors_per_sec", "value": n / (ms * 1e-3), "unit": "factors/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": wl["desc"], "l2": "192 MB buffer written between timed launches (outside the event pair)"}, "gpu_launches": int(launches),
+           "config": config_dict(wl, 1), "gpu_launches": int(launches), "kernel_ms": ms,
            "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
                         "note": "4 496 algorithmic B/factor; at 5k factors (22 MB) the launch is latency-sized: 22 MB at peak would take 3.4 us"},
            "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "factors/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int((hX.numel() + hR.numel() + hL.numel()) * 8),
                    "d2h_bytes_per_step": int((hE.numel() + hH1.numel() + hH2.numel()) * 8), "api": "cpi_imu_factor_eval_batch_host"}}
-    if not args.no_cpu_baseline:
+    # one Levenberg-Marquardt step of the IMU-only chain entirely on device: eval -> information blocks -> block-tridiagonal
+    # assembly -> block-cyclic-reduction Cholesky solve -> retract (parity unpinned: GTSAM is not in the tree)
+    if hasattr(factor, "chain_lm_step"):
+        try:
+            factor.chain_lm_step(model, dX, dR, dL); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(5):
+                factor.chain_lm_step(model, dX, dR, dL)
+            b.record(stream); torch.cuda.synchronize()
+            out["lm_step"] = {"ms": a.elapsed_time(b) / 5, "what": "eval + Hessian blocks + assemble + block-tridiagonal solve + retract, all on device", "keyframes": n + 1}
+        except Exception as ex:     # noqa: BLE001 -- reported, never hidden
+            out["lm_step"] = {"error": repr(ex)}
+    if cpu and not args.no_cpu_baseline:
         impl, kind = (Reference(), "reference") if Reference.available() else (Oracle(), "port")
-        cores = os.cpu_count() or 1
+        cores = synth.usable_cpus()
         impl.factor_eval(model, X, rec, L, nthreads=cores)
         t0 = time.perf_counter()
         for _ in range(5):
             impl.factor_eval(model, X, rec, L, nthreads=cores)
         dt = (time.perf_counter() - t0) / 5
         out["cpu_baseline"] = {"value": n / dt, "unit": "factors/s", "cores": cores, "kind": kind, "sample": f"{n} factors x 5 repeats, reference evaluateError with H1 and H2"}
-    print(json.dumps(out), flush=True)
+    if emit:
+        print(json.dumps(out), flush=True)
+    return out
+
+
+class Ctx:
+    """Process-wide state shared by the measurements of one bench run."""
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        from cpi_b200 import capi
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            torch.cuda.set_device(0)
+        capi.load()
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.comm = None
+        if self.world > 1:
+            from cpi_b200 import shard
+            self.comm = shard.Communicator()      # the product's NCCL communicator (C ABI)
+
+
+def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=False, clocks=True):
+    """One workload of the preintegration path on this process' GPU (all ranks call it together).  `distinct`: generate only
+    that many distinct windows on the host and tile them on the device (host generation is ~0.5 ms per window; the kernel does not
+    care, and the resident set still exceeds L2) -- the headline workload always uses all-distinct windows."""
+    import gc
+    import torch
+    import torch.distributed as dist
+    from cpi_b200 import capi, preint, synth
+    wl = WORKLOADS[name]
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    model, n, ns = wl["model"], wl["n"], wl["ns"]
+    rd = capi.REC_DOUBLES[model]
+    f32 = bool(wl.get("fp32"))
+    tdt, es = (torch.float32, 4) if f32 else (torch.float64, 8)
+    nd = n if not distinct else min(n, distinct)
+    reps = (n + nd - 1) // nd
+
+    # ---- resident inputs: NB distinct batches, NB * bytes > L2
+    bytes_in = n * ns * 7 * es + n * 13 * es
+    NB = 2 if bytes_in > 300e6 else min(8, max(2, int(np.ceil(300e6 / bytes_in))))
+    batches = []
+    for b in range(NB):
+        S, L = synth.make_windows(nd, ns, rate=wl["rate"], first_window=(rank * NB + b) * n)
+        dS, dL = torch.from_numpy(S).to(tdt).to(dev), torch.from_numpy(L).to(tdt).to(dev)
+        if reps > 1:
+            dS = dS.repeat(reps, 1, 1)[:n].contiguous(); dL = dL.repeat(reps, 1)[:n].contiguous()
+        batches.append((dS, dL))
+    del S, L      # NB: dropping a 112 MB numpy array is a ~12 ms munmap on the host -- must not happen inside the timed loop
+    # rank r's kernel writes gathers[k][r] in place; two buffers so that step i's all-gather overlaps step i+1's kernel
+    gathers = [torch.empty((world, n, rd), dtype=tdt, device=dev) for _ in range(2 if world > 1 else 1)]
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        dS, dL = batches[i % NB]
+        if world > 1:
+            ctx.comm.step(model, dS, dL, synth.SIGMAS, 0, gathers[i & 1], ns=ns, stream=stream)
+        else:
+            preint.preintegrate(model, dS, dL, synth.SIGMAS, 0, ns=ns, out=gathers[0][0], stream=stream)
+
+    # everything host-side (events, clock sampler) is set up BEFORE the warm-up so that the GPU goes from the warm-up
+    # steps straight into the timed region without an idle gap (see DESIGN.md "measurement notes").
+    sampler = ClockSampler(torch.cuda.current_device()) if (rank == 0 and clocks and not args.no_clocks) else None
+    if sampler:
+        sampler.start(); time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e in [ev0, ev1] + [x for pair in kev for x in pair]:
+        e.record(stream)                     # force the lazy cudaEventCreate now
+    # clock settle: the part idles at 120 MHz while the host generates inputs and needs ~20 ms of work (with a ~13 ms
+    # P-state stall in it, measured) to reach its load clocks; keep it busy for >= 150 ms before the W warm-up steps
+    t_settle = time.perf_counter()
+    k = 0
+    while time.perf_counter() - t_settle < 0.15:
+        step(k); k += 1
+        torch.cuda.synchronize()
+    for i in range(warmup):
+        step(i)
+    if world > 1:
+        ctx.comm.wait(stream)
+    launches0 = capi.launch_count()
+    gc.collect(); gc.disable()        # no collector pauses inside the timed region
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    ev0.record(stream)
+    for i in range(steps):
+        kev[i][0].record(stream)
+        step(warmup + i)
+        kev[i][1].record(stream)          # the all-gather is on the communicator's stream: this pair brackets the kernel alone
+    if world > 1:
+        ctx.comm.wait(stream)             # the timed region ends when the LAST all-gather has landed
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    t1 = time.time()
+    if world > 1:
+        dist.barrier()
+    launches = capi.launch_count() - launches0
+    gc.enable()
+    clk = sampler.stop(t0, t1) if sampler else None
+    total_ms = ev0.elapsed_time(ev1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    if os.environ.get("CPI_BENCH_DEBUG"):
+        print("kernel ms:", [round(a.elapsed_time(b), 3) for a, b in kev], file=sys.stderr)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    peaks, how = measured_peaks()
+    flops = wl["flops_per_sample"] * ns * n          # algorithmic flops per launch (SURVEY 8d contract)
+    ach_tf = flops / (kern_ms * 1e-3) * 1e-12
+    ach_gbs = wl["bytes_per_window"] * n / (kern_ms * 1e-3) * 1e-9
+    cfg = config_dict(wl, world)
+    if reps > 1:
+        cfg["inputs"] = f"{nd} distinct synthetic windows per batch, tiled x{reps} on the device"
+    out = {"metric": "imu_windows_per_sec", "value": value, "unit": "windows/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32 storage + f32 covariance RK4, f64 rotations/coefficients/means" if f32 else "f64", "data": "synthetic",
+           "config": cfg, "gpu_launches": int(launches), "kernel_ms": kern_ms,
+           "roofline": {"bound": "fp32+fp64 CUDA cores" if f32 else "fp64", "achieved": ach_tf, "peak": FFMA_PEAK_TFLOPS if f32 else DFMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                        "frac": ach_tf / (FFMA_PEAK_TFLOPS if f32 else DFMA_PEAK_TFLOPS),
+                        "traffic": NCU_TRAFFIC.get(name, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(name, (None, None))[1],
+                        "note": "CUDA-core FMA bound, not HBM/tensor (85 flop/B); peak = DFMA / FFMA microbenchmark measured on this pool (tools/microbench.cu, "
+                                "profiles/microbench_r02.jsonl); achieved = algorithmic flops (5.8 kflop/sample v1, 15 v2; SURVEY 8d) / CUDA-event kernel time "
+                                "(the executed fp64 instruction count is below that contract for v2 -- see DESIGN.md); traffic = DRAM bytes per launch of the "
+                                "committed ncu capture of this kernel, where one exists",
+                        "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"], "peak_source": how}},
+           "clocks": clk}
+
+    # ---- e2e through the C-ABI host entry point, pinned host buffers, H2D + kernel + D2H inside the timed region
+    if e2e and not args.no_e2e:
+        import ctypes
+        S, L = synth.make_windows(nd, ns, rate=wl["rate"], first_window=rank * n)
+        hS = torch.from_numpy(S).to(tdt); hL = torch.from_numpy(L).to(tdt)
+        if reps > 1:
+            hS = hS.repeat(reps, 1, 1)[:n].contiguous(); hL = hL.repeat(reps, 1)[:n].contiguous()
+        hS = hS.pin_memory(); hL = hL.pin_memory()
+        hO = torch.empty((n, rd), dtype=tdt).pin_memory()
+        del S, L
+        sig = np.ascontiguousarray(synth.SIGMAS)
+        lib = capi.load()
+
+        def host_step():
+            capi.check(lib.cpi_preintegrate_batch_host(model, 8 * es, n, None, ns, ctypes.c_void_p(hS.data_ptr()), ctypes.c_void_p(hL.data_ptr()),
+                                                       ctypes.c_void_p(sig.ctypes.data), 0, ctypes.c_void_p(hO.data_ptr())))
+        for _ in range(3):
+            host_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ke = max(3, min(steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            host_step()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / ke
+        if world > 1:
+            t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        out["e2e"] = {"value": world * n / (e2e_ms * 1e-3), "unit": "windows/s", "ms_per_step": e2e_ms,
+                      "h2d_bytes_per_step": int(hS.numel() * es + hL.numel() * es), "d2h_bytes_per_step": int(hO.numel() * es),
+                      "api": "cpi_preintegrate_batch_host (C ABI, pinned host buffers)"}
+        del hS, hL, hO
+    del batches, gathers
+    torch.cuda.empty_cache()
+
+    if cpu and rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = synth.usable_cpus()
+        v0, kind, cores, _ = cpu_arm(wl, max(2 * cores, 64))
+        sample = int(min(wl["n"], max(cores, v0 * 10.0)))
+        v, kind, cores, dt = cpu_arm(wl, sample)
+        out["cpu_baseline"] = {"value": v, "unit": "windows/s", "cores": cores, "cores_online": os.cpu_count(), "kind": kind,
+                               "sample": f"{sample} windows x {ns} samples of the same synthetic workload, {dt:.1f} s, "
+                                         + ("unmodified reference headers (oracle/_ref), std::thread over windows" if kind == "reference" else "oracle C port")}
+    return out
+
+
+def measure_single(ctx, args, wl):
+    """configs[0]: ONE 100-sample window -- for the GPU arm this is launch latency (one CTA, three lanes)."""
+    import torch
+    from cpi_b200 import preint, synth
+    S, L = synth.make_windows(1, wl["ns"], rate=wl["rate"], special=False)
+    dS, dL = torch.from_numpy(S).cuda(), torch.from_numpy(L).cuda()
+    out = torch.empty((1, 290), dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream()
+    for _ in range(20):
+        preint.preintegrate(1, dS, dL, synth.SIGMAS, 0, ns=wl["ns"], out=out, stream=stream)
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]
+    for a, b in evs:
+        a.record(stream); preint.preintegrate(1, dS, dL, synth.SIGMAS, 0, ns=wl["ns"], out=out, stream=stream); b.record(stream)
+    torch.cuda.synchronize()
+    ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
+    hS, hL = S.copy(), L.copy()
+    for _ in range(5):
+        preint.preintegrate_host(1, hS, hL, synth.SIGMAS, 0, ns=wl["ns"])
+    t0 = time.perf_counter()
+    for _ in range(50):
+        preint.preintegrate_host(1, hS, hL, synth.SIGMAS, 0, ns=wl["ns"])
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / 50
+    return {"metric": "imu_windows_per_sec", "value": 1e3 / ms, "unit": "windows/s", "kernel_ms": ms, "config": config_dict(wl, 1),
+            "roofline": {"frac": None, "note": "one window is a chain of 100 dependent samples on three lanes: pure latency, no roofline applies"},
+            "e2e": {"value": 1e3 / e2e_ms, "unit": "windows/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 100 * 56 + 104, "d2h_bytes_per_step": 2320}}
+
+
+def compact(name, r):
+    """Entry of the "configs" array: the numbers the judge asked for, not the whole line."""
+    if r is None:
+        return None
+    keep = {k: r.get(k) for k in ("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "kernel_ms", "dtype", "gpu_launches", "lm_step") if k in r}
+    keep["name"] = name
+    keep["workload"] = r["config"]["workload"]
+    if "inputs" in r["config"]:
+        keep["inputs"] = r["config"]["inputs"]
+    rf = r.get("roofline") or {}
+    keep["roofline"] = {k: rf.get(k) for k in ("bound", "achieved", "peak", "unit", "frac") if k in rf}
+    if "e2e" in r:
+        keep["e2e"] = r["e2e"]
+    return keep
 
 
 def main():
@@ -253,175 +517,53 @@ def main():
     ap.add_argument("--workload", default="v1_10k_200", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configs appended to the default line")
     ap.add_argument("--no-clocks", action="store_true", help="debug: do not poll nvidia-smi during the timed region")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if wl.get("factor"):
-        return run_factor(args, wl)
     if args.impl == "reference":
-        return run_reference(args, wl)
+        return run_factor(args, wl) if wl.get("factor") else run_reference(args, wl)
 
-    import torch
-    import torch.distributed as dist
-    from cpi_b200 import capi, preint, synth
+    ctx = Ctx()
+    if wl.get("factor"):
+        if ctx.rank == 0:
+            run_factor(args, wl)
+        return
+    if wl.get("single"):
+        if ctx.rank == 0:
+            r = measure_single(ctx, args, wl)
+            r.update({"n_gpus": 1, "steps": 50, "warmup": 20, "ms_per_step": r["kernel_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f64", "data": "synthetic", "gpu_launches": 50})
+            print(json.dumps(r), flush=True)
+        return
+    out = measure_preint(ctx, args.workload, args, args.steps, args.warmup, e2e=True, cpu=True)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    else:
-        torch.cuda.set_device(0)
-    capi.load()
-    dev = torch.device("cuda", torch.cuda.current_device())
-    model, n, ns = wl["model"], wl["n"], wl["ns"]
-    rd = capi.REC_DOUBLES[model]
-    f32 = bool(wl.get("fp32"))
-    tdt, es = (torch.float32, 4) if f32 else (torch.float64, 8)
-
-    # ---- resident inputs: NB distinct batches, NB * bytes > L2
-    bytes_in = n * ns * 7 * es + n * 13 * es
-    NB = min(8, max(2, int(np.ceil(300e6 / bytes_in))))
-    if bytes_in > 300e6:
-        NB = 2
-    batches = []
-    for b in range(NB):
-        S, L = synth.make_windows(n, ns, rate=wl["rate"], first_window=(rank * NB + b) * n)
-        batches.append((torch.from_numpy(S).to(tdt).to(dev), torch.from_numpy(L).to(tdt).to(dev)))
-    del S, L      # NB: dropping a 112 MB numpy array is a ~12 ms munmap on the host -- must not happen inside the timed loop
-    gather = torch.empty((world, n, rd), dtype=tdt, device=dev)     # rank r's kernel writes gather[r] in place
-    mine = gather[rank]
-    stream = torch.cuda.current_stream()
-
-    def step(i):
-        dS, dL = batches[i % NB]
-        preint.preintegrate(model, dS, dL, synth.SIGMAS, 0, ns=ns, out=mine, stream=stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gather.view(-1), mine.view(-1))
-
-    # everything host-side (events, clock sampler) is set up BEFORE the warm-up so that the GPU goes from the warm-up
-    # steps straight into the timed region without an idle gap (see DESIGN.md "measurement notes").
-    sampler = ClockSampler(torch.cuda.current_device()) if (rank == 0 and not args.no_clocks) else None
-    if sampler:
-        sampler.start(); time.sleep(0.3)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for e in [ev0, ev1] + [x for pair in kev for x in pair]:
-        e.record(stream)                     # force the lazy cudaEventCreate now
-    # clock settle: the part idles at 120 MHz while the host generates inputs and needs ~20 ms of work (with a ~13 ms
-    # P-state stall in it, measured) to reach its load clocks; keep it busy for >= 150 ms before the W warm-up steps
-    t_settle = time.perf_counter()
-    while time.perf_counter() - t_settle < 0.15:
-        step(0)
-        torch.cuda.synchronize()
-    for i in range(args.warmup):
-        step(i)
-    launches0 = capi.launch_count()
-    import gc
-    gc.collect(); gc.disable()        # no collector pauses inside the timed region
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.time()
-    ev0.record(stream)
-    for i in range(args.steps):
-        dS, dL = batches[(args.warmup + i) % NB]
-        kev[i][0].record(stream)
-        preint.preintegrate(model, dS, dL, synth.SIGMAS, 0, ns=ns, out=mine, stream=stream)
-        kev[i][1].record(stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gather.view(-1), mine.view(-1))
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    t1 = time.time()
-    if world > 1:
-        dist.barrier()
-    launches = capi.launch_count() - launches0
-    gc.enable()
-    clocks = sampler.stop(t0, t1) if sampler else None
-    total_ms = ev0.elapsed_time(ev1)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    if os.environ.get("CPI_BENCH_DEBUG"):
-        print("kernel ms:", [round(a.elapsed_time(b), 3) for a, b in kev], file=sys.stderr)
-        print("gaps ms:", [round(kev[i][1].elapsed_time(kev[i + 1][0]), 3) for i in range(len(kev) - 1)], file=sys.stderr)
-        print("head/tail ms:", round(ev0.elapsed_time(kev[0][0]), 3), round(kev[-1][1].elapsed_time(ev1), 3), file=sys.stderr)
-    if world > 1:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = world * n / (ms_per_step * 1e-3)
-
-    out = None
-    if rank == 0:
-        peaks, how = measured_peaks()
-        flops = wl["flops_per_sample"] * ns * n          # algorithmic flops per launch (SURVEY 8d contract)
-        ach_tf = flops / (kern_ms * 1e-3) * 1e-12
-        ach_gbs = wl["bytes_per_window"] * n / (kern_ms * 1e-3) * 1e-9
-        out = {"metric": "imu_windows_per_sec", "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f32 storage + f32 covariance RK4, f64 rotations/coefficients/means" if f32 else "f64", "data": "synthetic",
-               "config": {"workload": wl["desc"], "windows_per_gpu": n, "samples_per_window": ns, "model": f"CpiV{model}",
-                          "parallelism": f"window-sharded x{world}" + (", one NCCL all-gather of records per step" if world > 1 else ""),
-                          "l2": f"{NB} rotating resident input batches = {NB * bytes_in / 1e6:.0f} MB > 126 MB L2"},
-               "gpu_launches": int(launches),
-               "kernel_ms": kern_ms,
-               "roofline": {"bound": "fp32+fp64 CUDA cores" if f32 else "fp64", "achieved": ach_tf, "peak": FFMA_PEAK_TFLOPS if f32 else DFMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                            "frac": ach_tf / (FFMA_PEAK_TFLOPS if f32 else DFMA_PEAK_TFLOPS),
-                            "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
-                            "note": "CUDA-core FMA bound, not HBM/tensor (85 flop/B); peak = DFMA / FFMA microbenchmark measured on this pool (tools/microbench.cu, "
-                                    "profiles/microbench_r01.jsonl); achieved = algorithmic flops (5.8 kflop/sample v1, 15 v2; SURVEY 8d) / CUDA-event kernel time; "
-                                    "traffic = DRAM bytes per launch from the committed ncu capture (profiles/r01_k1_ws.txt) where one exists for this workload",
-                            "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"], "peak_source": how}},
-               "clocks": clocks}
-
-    # ---- e2e through the C-ABI host entry point, pinned host buffers, H2D + kernel + D2H inside the timed region
-    if not args.no_e2e:
-        S, L = synth.make_windows(n, ns, rate=wl["rate"], first_window=rank * n)
-        hS = torch.from_numpy(S).to(tdt).pin_memory(); hL = torch.from_numpy(L).to(tdt).pin_memory()
-        hO = torch.empty((n, rd), dtype=tdt).pin_memory()
-        del S, L
-        sig = np.ascontiguousarray(synth.SIGMAS)
-        lib = capi.load()
-        import ctypes
-
-        def host_step():
-            capi.check(lib.cpi_preintegrate_batch_host(model, 8 * es, n, None, ns, ctypes.c_void_p(hS.data_ptr()), ctypes.c_void_p(hL.data_ptr()),
-                                                       ctypes.c_void_p(sig.ctypes.data), 0, ctypes.c_void_p(hO.data_ptr())))
-        for _ in range(3):
-            host_step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ke = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            host_step()
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / ke
-        if world > 1:
-            t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
-        if rank == 0:
-            out["e2e"] = {"value": world * n / (e2e_ms * 1e-3), "unit": "windows/s", "ms_per_step": e2e_ms,
-                          "h2d_bytes_per_step": int(hS.numel() * es + hL.numel() * es), "d2h_bytes_per_step": int(hO.numel() * es),
-                          "api": "cpi_preintegrate_batch_host (C ABI, pinned host buffers)"}
-
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        v0, kind, cores, _ = cpu_arm(wl, max(2 * cores, 64))
-        sample = int(min(wl["n"], max(cores, v0 * 10.0)))
-        v, kind, cores, dt = cpu_arm(wl, sample)
-        out["cpu_baseline"] = {"value": v, "unit": "windows/s", "cores": cores, "kind": kind,
-                               "sample": f"{sample} windows x {ns} samples of the same synthetic workload, {dt:.1f} s, "
-                                         + ("unmodified reference headers (oracle/_ref), std::thread over windows" if kind == "reference" else "oracle C port")}
-    if rank == 0:
+    # ---- the other BASELINE configs, short runs, appended to the default line so that the driver's record carries them
+    if args.workload == "v1_10k_200" and not args.no_configs:
+        extra = []
+        k = max(3, min(args.steps, 10))
+        for name, distinct in (("v2_100k_400", 12_500), ("v1_1m_200_fp32", 12_500)):
+            try:
+                extra.append(compact(name, measure_preint(ctx, name, args, k, 3, distinct=distinct, e2e=(ctx.world == 1), cpu=False, clocks=False)))
+            except Exception as ex:     # noqa: BLE001 -- reported in the line, never hidden
+                extra.append({"name": name, "error": repr(ex)})
+        if ctx.rank == 0:
+            class A: pass
+            fa = A(); fa.__dict__.update(vars(args)); fa.steps = 20; fa.warmup = 3
+            for name, fn in (("factor_5k", lambda: run_factor(fa, WORKLOADS["factor_5k"], emit=False, cpu=False)),
+                             ("v1_single_100", lambda: measure_single(ctx, args, WORKLOADS["v1_single_100"]))):
+                try:
+                    extra.append(compact(name, fn()))
+                except Exception as ex:     # noqa: BLE001
+                    extra.append({"name": name, "error": repr(ex)})
+        out["configs"] = extra
+    if ctx.rank == 0:
         print(json.dumps(out), flush=True)
-    if world > 1:
+    if ctx.world > 1:
+        import torch.distributed as dist
+        if ctx.comm:
+            ctx.comm.close()
         dist.destroy_process_group()
 
 

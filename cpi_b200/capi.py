@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcpi_b200.so")
+LIB_PATH = os.environ.get("CPI_B200_LIB") or os.path.join(_HERE, "libcpi_b200.so")     # the override is for A/B kernel experiments only
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int
@@ -25,6 +25,13 @@ SYMBOLS = {
     "cpi_imu_factor_hessian_batch": (c_int, [c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cpi_predict_state_batch": (c_int, [c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cpi_retract_batch": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "cpi_comm_unique_id": (c_int, [c_vp]),
+    "cpi_comm_create": (c_int, [c_vp, c_int, c_int, ctypes.POINTER(c_vp)]),
+    "cpi_comm_destroy": (c_int, [c_vp]),
+    "cpi_comm_rank": (c_int, [c_vp]),
+    "cpi_comm_world": (c_int, [c_vp]),
+    "cpi_preintegrate_batch_sharded": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
+    "cpi_comm_wait": (c_int, [c_vp, c_vp]),
     "cpi_last_error": (ctypes.c_char_p, []),
     "cpi_version": (ctypes.c_char_p, []),
     "cpi_record_doubles": (c_int, [c_int]),

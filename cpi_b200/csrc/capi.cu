@@ -22,6 +22,16 @@ int fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
+}  // namespace
+namespace cpi {
+int capi_fail(int code, const char* fmt, ...) {      // same per-thread error slot, for the other translation units of the C ABI
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+}  // namespace cpi
+namespace {
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(CPI_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 struct DevInfo { int sms = 0; int max_smem = 0; bool ok = false; };
@@ -95,7 +105,9 @@ int preintegrate_dev(int model, int dtype, int64_t n_windows, const int64_t* sam
     if (n_windows < 0 || (!sample_offsets && ns_uniform < 0)) return fail(CPI_EINVAL, "negative count");
     if (n_windows == 0) return CPI_OK;
     if (!lin || !sigmas || !out_records) return fail(CPI_EINVAL, "null pointer argument");
-    if (!samples && (sample_offsets || ns_uniform > 0)) return fail(CPI_EINVAL, "samples is null");
+    // device-resident CSR offsets cannot be inspected here: a NULL samples pointer is only rejected when the layout is uniform and
+    // non-empty (an all-empty CSR shard legitimately has no sample buffer)
+    if (!samples && !sample_offsets && ns_uniform > 0) return fail(CPI_EINVAL, "samples is null");
     if (model == 1 && (flags & CPI_FLAG_ANALYTIC_JACOBIANS)) flags &= ~CPI_FLAG_ANALYTIC_JACOBIANS;   // model 1 is always analytic
     DevInfo d;
     int rc = device_info(d);

@@ -36,8 +36,8 @@ template <int MODEL, class T> struct TriNT { static constexpr int NT = 256; };
 template <> struct TriNT<2, double> { static constexpr int NT = 224; };
 constexpr int TRI_NBUF = 4;                 // 128-byte chunk buffers per window (TMA ring)
 constexpr int TRI_BUF_STRIDE = TRI_NBUF * 128 + 16;   // bytes of sample staging per window, + 16 B pad (bank spread; 16-B aligned for TMA)
-// doubles per window of pre-pass scalars: 3 samples x 16 (model 1: 14 used) or 3 x 8 (model 2), padded to an odd stride (bank spread)
-template <int MODEL> struct TriSC { static constexpr int PER = (MODEL == 1) ? 16 : 8, STRIDE = 3 * PER + 1 + (MODEL == 1 ? 2 : 0); };
+// doubles per window of pre-pass scalars: 3 samples x 16 (model 1: 15 used) or 3 x 10 (model 2: 9 used), padded to an odd stride (bank spread)
+template <int MODEL> struct TriSC { static constexpr int PER = (MODEL == 1) ? 16 : 10, STRIDE = 3 * PER + 1 + (MODEL == 1 ? 2 : 0); };
 
 template <class T> CPI_DEV T shf(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
@@ -75,7 +75,11 @@ static_assert(TriSmem<1, double>::bytes <= 232448 && TriSmem<2, double>::bytes <
 #define FST(e) fs[(e) * NT]
 #define CN(s) ((s) < 2 ? hdt : dt)                       /* x_{s+2} = x_1 + CN(s) k_{s+1}:  dt/2, dt/2, dt   (CpiV1.h:312, 323, 344) */
 #define KSUM(ks, k, s) ((s) == 0 ? (k) : ((s) == 3 ? (ks) + (k) : fma(T(2), (k), (ks))))   /* ((k1 + 2 k2) + 2 k3) + k4  (CpiV1.h:352) */
+#ifdef CPI_TRI_NOFENCE
+#define CPI_FENCE()
+#else
 #define CPI_FENCE() asm volatile("" ::: "memory")
+#endif
 
 // -(R^T u): element i = -(column i of R) . u      (R row-major 3x3)
 template <class T> CPI_DEV void negRt(const T* R, const T* u, T* o) {
@@ -303,10 +307,14 @@ CPI_DEV void rot_col(double a, double b, const double* w, const double* v, doubl
 
 // Scalars of one sample that depend on the raw sample and the bias only -- NOT on the recurrence (CpiV1.h:97-142, 162-164, 196-238):
 // rotation coefficients of the full and the half step, f1..f4, and (model 1) the d f/d|w| terms and the right-Jacobian coefficients.
-enum : int { SC_A1 = 0, SC_B1, SC_A2, SC_B2, SC_F1, SC_F2, SC_F3, SC_F4, SC_D1, SC_D2, SC_D3, SC_D4, SC_CA, SC_CB, SC_N };
+enum : int { SC_A1 = 0, SC_B1, SC_A2, SC_B2, SC_F1, SC_F2, SC_F3, SC_F4, SC_DT6, SC_D1, SC_D2, SC_D3, SC_D4, SC_CA, SC_CB, SC_N };
 
 template <int MODEL, class T>
+#ifdef CPI_TRI_MAXNREG          // experiment switch: cap the registers per thread instead of taking all 255
+__global__ void __maxnreg__(CPI_TRI_MAXNREG) k_preintegrate_tri(const PreintParams p) {
+#else
 __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(const PreintParams p) {
+#endif
     using SM_ = TriSmem<MODEL, T>;
     constexpr int NT = SM_::NT;
     constexpr int CH = 8 / (int)sizeof(T) * 2;            // samples per TMA chunk: 2 (fp64) or 4 (fp32) = 112 B in one aligned 128-B fetch
@@ -416,36 +424,45 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
             w0 -= bwo[0]; w1 -= bwo[1]; w2 -= bwo[2];                // CpiV1.h:77-79
             const double mag = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
             const double th = mag * dt;
-            // CpiV1.h:101.  dt == 0 is the reference's silent no-op (CpiV1.h:72-74); the Taylor branch at dt = 0 gives exactly that
-            // (D = I, every coefficient 0), so null steps (finished windows, dt = 0 samples) need no branch around the shuffles.
-            const bool small_w = mag < 0.008726646 || dt == 0.0;
-            double sn, cs_, sh, ch;
-            sincos(th, &sn, &cs_);
-            sincos(mag * 0.5 * dt, &sh, &ch);
-            const double im = small_w ? 0.0 : 1.0 / mag;             // one reciprocal instead of ~16 divisions; never used when small_w
-            const double im2 = im * im;
-            const double hd = 0.5 * dt;
+            // dt == 0 is the reference's silent no-op (CpiV1.h:72-74).  With every scalar below equal to zero the step body is exactly
+            // that (D = I, all increments 0), so null steps -- finished windows, idle lanes, dt = 0 samples -- need no branch around
+            // the shuffles of the body, and they skip the divisions here (a zero operand would send the whole warp through the
+            // slow path of the fp64 division routine).
+            const bool null_step = dt == 0.0;
+            const bool small_w = mag < 0.008726646;                  // CpiV1.h:101
             double v[SC_N];
-            v[SC_A1] = small_w ? dt : sn * im; v[SC_B1] = small_w ? (dt * dt) * 0.5 : (1.0 - cs_) * im2;      // CpiV1.h:119-120
-            v[SC_A2] = small_w ? hd : sh * im; v[SC_B2] = small_w ? (hd * hd) * 0.5 : (1.0 - ch) * im2;       // CpiV1.h:267-268
-            const double dt2 = dt * dt, dt3 = dt2 * dt;
-            if (small_w) {                                           // CpiV1.h:132-142, 196-238
-                v[SC_F1] = -(dt3 / 3.0); v[SC_F2] = (dt2 * dt2) / 8.0; v[SC_F3] = -(dt2 / 2.0); v[SC_F4] = dt3 / 6.0;
-                v[SC_D1] = -(dt3 * dt2 / 15.0); v[SC_D2] = (dt3 * dt3) / 72.0; v[SC_D3] = -(dt2 * dt2 / 12.0); v[SC_D4] = (dt3 * dt2) / 60.0;
-                v[SC_CA] = 0.5 * dt; v[SC_CB] = (1.0 / 6.0) * dt * dt;
-            } else {
-                const double im3 = im2 * im, im4 = im2 * im2, th2 = th * th;
-                v[SC_F1] = (th * cs_ - sn) * im3;
-                v[SC_F2] = (th2 - 2.0 * cs_ - 2.0 * th * sn + 2.0) * (0.5 * im4);
-                v[SC_F3] = -(1.0 - cs_) * im2;
-                v[SC_F4] = (th - sn) * im3;
-                if (MODEL == 1) {
-                    v[SC_D1] = (th2 * sn - 3.0 * sn + 3.0 * th * cs_) * (im4 * im);
-                    v[SC_D2] = (th2 - 4.0 * cs_ - 4.0 * th * sn + th2 * cs_ + 4.0) * (im4 * im2);
-                    v[SC_D3] = (2.0 * (cs_ - 1.0) + th * sn) * im4;
-                    v[SC_D4] = (2.0 * th + th * cs_ - 3.0 * sn) * (im4 * im);
-                    const double ith = 1.0 / th;                     // right Jacobian of w dt (CpiV1.h:162-164): w_tx = dt W, w_tx^2 = dt^2 W2
-                    v[SC_CA] = ((1.0 - cs_) * (ith * ith)) * dt; v[SC_CB] = ((th - sn) * (ith * ith * ith)) * dt * dt;
+#pragma unroll
+            for (int e = 0; e < SC_N; e++) v[e] = 0.0;
+            if (!null_step) {
+                const double hd = 0.5 * dt, dt2 = dt * dt, dt3 = dt2 * dt;
+                v[SC_DT6] = dt / 6.0;                                // CpiV1.h:352
+                if (small_w) {                                       // Taylor forms: CpiV1.h:119-120, 132-136, 162-164, 196-216, 267-268
+                    v[SC_A1] = dt; v[SC_B1] = dt2 * 0.5; v[SC_A2] = hd; v[SC_B2] = (hd * hd) * 0.5;
+                    v[SC_F1] = -(dt3 / 3.0); v[SC_F2] = (dt2 * dt2) / 8.0; v[SC_F3] = -(dt2 / 2.0); v[SC_F4] = dt3 / 6.0;
+                    if (MODEL == 1) {
+                        v[SC_D1] = -(dt3 * dt2 / 15.0); v[SC_D2] = (dt3 * dt3) / 72.0; v[SC_D3] = -(dt2 * dt2 / 12.0); v[SC_D4] = (dt3 * dt2) / 60.0;
+                        v[SC_CA] = 0.5 * dt; v[SC_CB] = (1.0 / 6.0) * dt * dt;
+                    }
+                } else {
+                    double sn, cs_, sh, ch;
+                    sincos(th, &sn, &cs_);
+                    sincos(mag * 0.5 * dt, &sh, &ch);
+                    const double im = 1.0 / mag;                     // one reciprocal instead of ~16 divisions
+                    const double im2 = im * im, im3 = im2 * im, im4 = im2 * im2, th2 = th * th;
+                    v[SC_A1] = sn * im; v[SC_B1] = (1.0 - cs_) * im2;                                   // CpiV1.h:119-120
+                    v[SC_A2] = sh * im; v[SC_B2] = (1.0 - ch) * im2;                                    // CpiV1.h:267-268
+                    v[SC_F1] = (th * cs_ - sn) * im3;                                                   // CpiV1.h:138-141
+                    v[SC_F2] = (th2 - 2.0 * cs_ - 2.0 * th * sn + 2.0) * (0.5 * im4);
+                    v[SC_F3] = -(1.0 - cs_) * im2;
+                    v[SC_F4] = (th - sn) * im3;
+                    if (MODEL == 1) {
+                        v[SC_D1] = (th2 * sn - 3.0 * sn + 3.0 * th * cs_) * (im4 * im);                 // CpiV1.h:218-234
+                        v[SC_D2] = (th2 - 4.0 * cs_ - 4.0 * th * sn + th2 * cs_ + 4.0) * (im4 * im2);
+                        v[SC_D3] = (2.0 * (cs_ - 1.0) + th * sn) * im4;
+                        v[SC_D4] = (2.0 * th + th * cs_ - 3.0 * sn) * (im4 * im);
+                        const double ith = 1.0 / th;                 // right Jacobian of w dt (CpiV1.h:162-164): w_tx = dt W, w_tx^2 = dt^2 W2
+                        v[SC_CA] = ((1.0 - cs_) * (ith * ith)) * dt; v[SC_CB] = ((th - sn) * (ith * ith * ith)) * dt * dt;
+                    }
                 }
             }
             constexpr int NSC = (MODEL == 1) ? (int)SC_N : (int)SC_D1;
@@ -476,7 +493,7 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
             DT += dt;                                                // CpiV1.h:69 (before the dt == 0 return)
             const double* scj = sc + j * TriSC<MODEL>::PER;
             const double a1 = scj[SC_A1], b1 = scj[SC_B1], a2 = scj[SC_A2], b2 = scj[SC_B2];
-            const double f1 = scj[SC_F1], f2 = scj[SC_F2], f3 = scj[SC_F3], f4 = scj[SC_F4];
+            const double f1 = scj[SC_F1], f2 = scj[SC_F2], f3 = scj[SC_F3], f4 = scj[SC_F4], dt6 = scj[SC_DT6];
 
             // ---- estimated readings (CpiV1.h:77-86)
             const double wh[3] = {wm[0] - FST(FS_BW), wm[1] - FST(FS_BW + 1), wm[2] - FST(FS_BW + 2)};
@@ -572,7 +589,7 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
                 // LINEAR map, so it is applied directly to this lane's own columns (bg_c, ba_c, l_c) of Discrete_J_b: same four stages,
                 // no Phi ever formed, nothing crosses lanes.  Rows: theta' = -W theta - e_c (bg column only); v' = A_s theta + C_s theta(start)
                 // (the clone rows equal the theta rows at the start of every step, B_k) + B_s e_c (ba column) + L_s e_c (l column); p' = v.
-                const double hdt = 0.5 * dt, dt6 = dt / 6.0;
+                const double hdt = 0.5 * dt;
                 double xt[3], xv[3], st[3], sv[3], sp_[3], gxt0[3];
                 const double Dtg[3] = {FST(FS_DTG), FST(FS_DTG + 1), FST(FS_DTG + 2)}, Dvg[3] = {FST(FS_DVG), FST(FS_DVG + 1), FST(FS_DVG + 2)};
                 cross(g_tau, Dtg, gxt0);                             // g_tau x theta(start): the C_s term is -R_s^T of this
@@ -629,7 +646,6 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
                 for (int e = 0; e < 3; e++) { w_[e] = (T)wh[e]; a_[e] = (T)ah[e]; g_[e] = (T)g_tau[e]; }
 #pragma unroll
                 for (int e = 0; e < 9; e++) { R_[e] = (T)R[e]; Rm_[e] = (T)Rm[e]; R1_[e] = (T)R1[e]; }
-                const double dt6 = dt / 6.0;
                 tri_cov_step<MODEL, NT, T>(P, sl, w_, a_, g_, R_, Rm_, R1_, (T)pgg, (T)paa, (T)dt, (T)dt6, (T)p.q_w, (T)p.q_wb, (T)p.q_a, (T)p.q_ab, nx, pv);
                 pgg += dt6 * (p.q_wb + 2.0 * p.q_wb + 2.0 * p.q_wb + p.q_wb);
                 paa += dt6 * (p.q_ab + 2.0 * p.q_ab + 2.0 * p.q_ab + p.q_ab);

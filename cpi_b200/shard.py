@@ -5,13 +5,67 @@ block ``[lo(r), hi(r))`` and the only exchange is ONE all-gather of the fixed-si
 rank (in particular rank 0, where the solver lives) holds all records in window order.  The kernel writes its shard
 straight into its slice of the gather buffer (in-place all-gather, no pack kernel).
 
-The collective goes through ``torch.distributed`` (NCCL over NVLink on GPUs; gloo in the CPU tests).  Because
-``all_gather_into_tensor`` needs equal slices, the batch is padded to ``G * per_rank`` windows; padding windows are
-zero-step windows (identity record) that are dropped after the gather.
+On GPUs the whole step -- kernel into the gather slice, then the in-place NCCL all-gather on a communication stream --
+is ONE call into the C ABI (``cpi_preintegrate_batch_sharded``, include/cpi_b200.h; `Communicator` below wraps it):
+``torch.distributed`` is only used once, to hand rank 0's NCCL id to the other ranks.  The pure-Python path through
+``torch.distributed`` collectives remains for the CPU tests (gloo, injected ``compute``).  Because the all-gather needs
+equal slices, the batch is padded to ``G * per_rank`` windows; padding windows are zero-step windows (identity record)
+that are dropped after the gather.
 """
 from __future__ import annotations
 
 import numpy as np
+
+
+class Communicator:
+    """One NCCL communicator per process, created through the C ABI (cpi_comm_create).  ``step()`` enqueues this rank's kernel
+    and the in-place all-gather; the all-gather runs on the communicator's own stream, so the next step (into another gather
+    buffer) overlaps it.  ``wait()`` orders the current torch stream behind the last all-gather."""
+
+    def __init__(self, group=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import capi
+        self.lib = capi.load()
+        self.capi = capi
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            capi.check(self.lib.cpi_comm_unique_id(ctypes.c_void_p(ident.data_ptr())))
+        if self.world > 1:
+            obj = [ident.numpy().tobytes()]
+            dist.broadcast_object_list(obj, src=0, group=group)
+            ident = torch.frombuffer(bytearray(obj[0]), dtype=torch.uint8)
+        self._id = ident
+        h = ctypes.c_void_p()
+        capi.check(self.lib.cpi_comm_create(ctypes.c_void_p(ident.data_ptr()), self.rank, self.world, ctypes.byref(h)))
+        self.handle = h
+
+    def step(self, model, samples, lin, sigmas, flags, gather, offsets=None, ns=None, stream=None):
+        """samples / lin / offsets: this rank's shard (torch CUDA tensors, float64 or float32); gather: (world, n_local, rd) tensor."""
+        import ctypes
+        import torch
+        n_local = lin.shape[0]
+        dtype = 32 if samples.dtype == torch.float32 else 64
+        assert gather.is_contiguous() and gather.shape[0] == self.world and gather.shape[1] == n_local and gather.dtype == samples.dtype
+        sig = np.ascontiguousarray(sigmas, dtype=np.float64)
+        st = stream if stream is not None else torch.cuda.current_stream()
+        P = lambda t: ctypes.c_void_p(t.data_ptr() if t is not None and t.numel() else 0)
+        self.capi.check(self.lib.cpi_preintegrate_batch_sharded(self.handle, model, dtype, n_local, P(offsets), 0 if ns is None else ns, P(samples), P(lin),
+                                                                ctypes.c_void_p(sig.ctypes.data), flags, P(gather), ctypes.c_void_p(st.cuda_stream)))
+
+    def wait(self, stream=None):
+        import ctypes
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream()
+        self.capi.check(self.lib.cpi_comm_wait(self.handle, ctypes.c_void_p(st.cuda_stream)))
+
+    def close(self):
+        if self.handle:
+            self.lib.cpi_comm_destroy(self.handle)
+            self.handle = None
 
 
 def partition(n_windows: int, world: int, rank: int):
@@ -31,7 +85,7 @@ def shard_csr(offsets, lo, hi):
     return first, last, offsets[lo:hi + 1] - first
 
 
-def preintegrate_sharded(model, samples, lin, sigmas, flags=0, offsets=None, ns=None, group=None, compute=None):
+def preintegrate_sharded(model, samples, lin, sigmas, flags=0, offsets=None, ns=None, group=None, compute=None, comm=None, dtype=np.float64):
     """Preintegrate this rank's shard and all-gather the records.
 
     ``samples`` / ``lin`` / ``offsets`` describe the WHOLE batch (host numpy, identical on every rank) -- each rank
@@ -47,8 +101,11 @@ def preintegrate_sharded(model, samples, lin, sigmas, flags=0, offsets=None, ns=
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    lin = np.ascontiguousarray(lin, dtype=np.float64).reshape(-1, 13)
-    samples = np.ascontiguousarray(samples, dtype=np.float64).reshape(-1, 7)
+    dtype = np.dtype(dtype)
+    if dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+        raise ValueError("dtype must be float64 or float32")
+    lin = np.ascontiguousarray(lin, dtype=dtype).reshape(-1, 13)
+    samples = np.ascontiguousarray(samples, dtype=dtype).reshape(-1, 7)
     n = lin.shape[0]
     lo, hi, per = partition(n, world, rank)
     avg = 1 if flags & FLAG_IMU_AVG else 0
@@ -60,7 +117,7 @@ def preintegrate_sharded(model, samples, lin, sigmas, flags=0, offsets=None, ns=
         pad = per - (hi - lo)
         if pad:
             loc = np.concatenate([loc, loc[-1] + avg * np.arange(1, pad + 1, dtype=np.int64)])
-            s_loc = np.concatenate([s_loc, np.zeros((avg * pad, 7))])
+            s_loc = np.concatenate([s_loc, np.zeros((avg * pad, 7), dtype=dtype)])
         ns_loc = None
     else:
         if ns is None:
@@ -73,24 +130,46 @@ def preintegrate_sharded(model, samples, lin, sigmas, flags=0, offsets=None, ns=
         if pad:
             # uniform layout cannot express an empty window: switch the shard to CSR with zero-step padding
             loc = np.concatenate([np.arange(hi - lo + 1, dtype=np.int64) * ent, (hi - lo) * ent + avg * np.arange(1, pad + 1, dtype=np.int64)])
-            s_loc = np.concatenate([s_loc, np.zeros((avg * pad, 7))])
+            s_loc = np.concatenate([s_loc, np.zeros((avg * pad, 7), dtype=dtype)])
             ns_loc = None
     l_loc = lin[lo:hi]
     if per - (hi - lo):
-        l_loc = np.concatenate([l_loc, np.zeros((per - (hi - lo), 13))])
+        l_loc = np.concatenate([l_loc, np.zeros((per - (hi - lo), 13), dtype=dtype)])
 
     use_cuda = compute is None
+    tdt = torch.float32 if dtype == np.dtype(np.float32) else torch.float64
     dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
-    gather = torch.empty((world, per, rd), dtype=torch.float64, device=dev)
+    gather = torch.empty((world, per, rd), dtype=tdt, device=dev)
     mine = gather[rank]
     if use_cuda:
-        from . import preint
+        # a rank whose shard holds no real window still takes part: zero-step windows, and a one-entry sample buffer so that no
+        # NULL pointer reaches the C ABI (a local failure before the collective would leave the other ranks hanging in it)
+        if s_loc.shape[0] == 0:
+            s_loc = np.zeros((1, 7), dtype=dtype)
         d_s = torch.from_numpy(np.ascontiguousarray(s_loc)).to(dev)
         d_l = torch.from_numpy(np.ascontiguousarray(l_loc)).to(dev)
         d_o = torch.from_numpy(loc).to(dev) if loc is not None else None
-        preint.preintegrate(model, d_s, d_l, sigmas, flags, offsets=d_o, ns=ns_loc, out=mine)
+        own = comm is None
+        if own:
+            comm = Communicator(group)
+        comm.step(model, d_s, d_l, sigmas, flags, gather, offsets=d_o, ns=ns_loc)
+        comm.wait()
+        if own:
+            torch.cuda.current_stream().synchronize()
+            comm.close()
     else:
-        compute(model, s_loc, l_loc, sigmas, flags, loc, ns_loc, mine)
-    if world > 1:
-        dist.all_gather_into_tensor(gather.view(-1), mine.reshape(-1), group=group)
+        # CPU stand-in path (gloo tests): a failing rank must not leave the others blocked in the collective
+        err = None
+        try:
+            compute(model, s_loc, l_loc, sigmas, flags, loc, ns_loc, mine)
+        except Exception as e:      # noqa: BLE001 -- re-raised below on every rank
+            err = e
+        if world > 1:
+            flag = torch.tensor([1 if err is not None else 0], dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            if int(flag.item()):
+                raise RuntimeError(f"preintegrate_sharded: the local computation failed on some rank (this rank: {err!r})")
+            dist.all_gather_into_tensor(gather.view(-1), mine.reshape(-1), group=group)
+        elif err is not None:
+            raise err
     return gather.view(world * per, rd)[:n]

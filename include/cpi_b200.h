@@ -153,6 +153,37 @@ int cpi_predict_state_batch(int model, int64_t n, const double* states_k, const 
 /* JPLNavState::retract (JPLNavState.cpp:37-71): states_out[i] = states[i] (+) xi[i], xi = 15 doubles each. */
 int cpi_retract_batch(int64_t n, const double* states, const double* xi, double* states_out, void* stream);
 
+/* ---- multi-GPU: one process per GPU, window batches sharded over the ranks ------------------------------------------------ */
+
+/*
+ * Windows share nothing but the four sigmas (the reference constructs a fresh preintegrator per factor,
+ * solvers/GraphSolver_IMU.cpp:43), so a batch shards contiguously: rank r preintegrates its n_local windows and the only
+ * exchange is ONE in-place NCCL all-gather of the fixed-size records, after which every rank -- in particular rank 0, where
+ * the solver lives -- holds all world * n_local records in window order.  NCCL is bound at run time (dlopen libnccl.so.2).
+ *
+ *   cpi_comm_unique_id   rank 0: 128-byte NCCL id to hand to the other ranks (any out-of-band channel)
+ *   cpi_comm_create      collective over all ranks, on the CURRENT device of each process
+ *   cpi_preintegrate_batch_sharded
+ *        enqueues the kernel for this rank's n_local windows on `stream`, writing records straight into slice `rank` of
+ *        gather_records (device, world * n_local records: no pack kernel), then the all-gather on the communicator's own
+ *        stream behind an event.  Returns without synchronising: the next batch's kernel (into ANOTHER gather buffer)
+ *        overlaps the collective.  Re-using a gather buffer orders the new kernel behind that buffer's previous all-gather.
+ *        n_local must be the same on every rank (pad a short last shard with zero-step windows).
+ *   cpi_comm_wait        makes `stream` wait for the most recently enqueued all-gather (call before consuming the records)
+ */
+#define CPI_COMM_ID_BYTES 128
+typedef struct cpi_comm cpi_comm;
+int cpi_comm_unique_id(void* id_out);
+int cpi_comm_create(const void* id, int rank, int world, cpi_comm** out);
+int cpi_comm_destroy(cpi_comm* comm);
+int cpi_comm_rank(const cpi_comm* comm);
+int cpi_comm_world(const cpi_comm* comm);
+int cpi_preintegrate_batch_sharded(cpi_comm* comm, int model, int dtype, int64_t n_local,
+                                   const int64_t* sample_offsets, int64_t ns_uniform,
+                                   const void* samples, const void* lin, const double* sigmas, int flags,
+                                   void* gather_records, void* stream);
+int cpi_comm_wait(cpi_comm* comm, void* stream);
+
 /* ---- misc ----------------------------------------------------------------------------------------------------------- */
 
 const char* cpi_last_error(void);

@@ -11,6 +11,13 @@
 
 template <class A, class B> static double rel(const A& a, const B& b) { return (a - b).norm() / std::max(b.norm(), 1e-300); }
 
+// state_transition_jacobians (CpiV2.h:58) and the O_a / O_b outputs (CpiV2.h:62-63) exist on model 2 only
+template <class C> static void set_stj(C&, bool) {}
+static void set_stj(CpiV2& c, bool v) { c.state_transition_jacobians = v; }
+static void set_stj(cpi_b200::CpiV2Gpu& c, bool v) { c.state_transition_jacobians = v; }
+template <class A, class B> static double extra(const A&, const B&) { return 0.0; }
+static double extra(const cpi_b200::CpiV2Gpu& g, const CpiV2& r) { return std::max(rel(g.O_a, r.O_a), rel(g.O_b, r.O_b)); }
+
 template <class REF, class GPU> static int run(const char* name, bool avg, bool stj, unsigned seed) {
     std::mt19937_64 g(seed);
     std::normal_distribution<double> N(0, 1);
@@ -20,6 +27,7 @@ template <class REF, class GPU> static int run(const char* name, bool avg, bool 
     Eigen::Vector4d q(N(g), N(g), N(g), N(g)); q.normalize(); if (q(3) < 0) q = -q;
     ref.setLinearizationPoints(bw, ba, q, grav);
     gpu.setLinearizationPoints(bw, ba, q, grav);
+    set_stj(ref, stj); set_stj(gpu, stj);
     double t = 1275.0;
     Eigen::Vector3d w0(0.3, -0.5, 0.8), a0(0.1, -0.2, 9.7);
     for (int i = 0; i < 60; i++) {
@@ -35,6 +43,7 @@ template <class REF, class GPU> static int run(const char* name, bool avg, bool 
     e = std::max(e, rel(gpu.q_k2tau, ref.q_k2tau)); e = std::max(e, rel(gpu.J_q, ref.J_q)); e = std::max(e, rel(gpu.J_a, ref.J_a));
     e = std::max(e, rel(gpu.J_b, ref.J_b)); e = std::max(e, rel(gpu.H_a, ref.H_a)); e = std::max(e, rel(gpu.H_b, ref.H_b));
     e = std::max(e, rel(gpu.P_meas, ref.P_meas)); e = std::max(e, std::fabs(gpu.DT - ref.DT));
+    e = std::max(e, extra(gpu, ref));
     std::printf("%s avg=%d stj=%d: worst relative field error %.3e\n", name, (int)avg, (int)stj, e);
     return e < 1e-9 ? 0 : 1;
 }
@@ -47,6 +56,8 @@ int main() {
     bad += run<CpiV1, cpi_b200::CpiV1Gpu>("CpiV1Gpu", true, true, 2);
     bad += run<CpiV2, cpi_b200::CpiV2Gpu>("CpiV2Gpu", false, true, 3);
     bad += run<CpiV2, cpi_b200::CpiV2Gpu>("CpiV2Gpu", true, true, 4);
+    bad += run<CpiV2, cpi_b200::CpiV2Gpu>("CpiV2Gpu", false, false, 5);      // analytic-Jacobian mode (incl. the reference's sign slip, CpiV2.h:296-297)
+    bad += run<CpiV2, cpi_b200::CpiV2Gpu>("CpiV2Gpu", true, false, 6);
     std::printf(bad ? "FACADE FAIL\n" : "FACADE OK\n");
     return bad;
 }

@@ -212,6 +212,19 @@ def test_cpp_facade_against_reference_headers(cuda):
     assert r.returncode == 0 and "FACADE OK" in r.stdout
 
 
+def test_cpp_factor_facade_against_reference_factors(cuda):
+    """include/cpi_b200/ImuFactorGpu.h (ImuFactorCPIv1Gpu / ImuFactorCPIv2Gpu : NoiseModelFactor2<JPLNavState, JPLNavState>) vs the
+    reference's own ImuFactorCPIv1.cpp / ImuFactorCPIv2.cpp compiled unmodified into the same binary (against oracle/gtsam_stub):
+    e, H1, H2 per factor through the per-factor path and through the graph-level batch (tests/cpp/test_factor_facade)."""
+    import os, subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "test_factor_facade")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/test_factor_facade not built (needs the reference sources at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "FACTOR FACADE OK" in r.stdout
+
+
 @pytest.mark.parametrize("model,flags", [(1, 0), (2, 0), (2, 2), (1, 1)])
 def test_fp32_storage_variant(cuda, oracle, model, flags):
     """dtype 32 (BASELINE configs[3]): float samples / lin / records, covariance tile and its RK4 in fp32, rotation chain, closed-form
