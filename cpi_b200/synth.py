@@ -177,31 +177,30 @@ def parse_imu_dat(text_or_path):
     return 1e-3 * d[:, 7], d[:, 0:3].copy(), d[:, 3:6].copy()
 
 
-def cut_windows(t, w, a, update_times):
-    """Replay the reference driver loop (solvers/GraphSolver_IMU.cpp:50-69) over an IMU stream.
+def cut_windows(t, w, a, update_times, imu_wait=0):
+    """Replay the reference driver loop (solvers/GraphSolver_IMU.cpp:50-69) over an IMU stream: the C ABI's host-side window
+    builder ``cpi_cut_windows`` (include/cpi_b200.h; cpi_b200/csrc/windows.cu).
 
     For every camera/update time (ascending), consume IMU readings while ``imu_times[1] <= updatetime`` -- one step
     feed_IMU(t0, t1, w0, a0) per reading with dt >= 0 -- then, if ``updatetime - imu_times[0] > 0``, one partial step
-    feed_IMU(t0, updatetime, w0, a0) and set imu_times[0] = updatetime.  Returns (samples[total,7], offsets[n+1]) in the
+    feed_IMU(t0, updatetime, w0, a0) and set imu_times[0] = updatetime.  ``imu_wait`` > 0 adds the reference's initialisation
+    (the first update that finds that many queued readings emits no window).  Returns (samples[total,7], offsets[n+1]) in the
     CSR layout of include/cpi_b200.h (imu_avg = False, as at the call site GraphSolver_IMU.cpp:45).
     """
-    t = np.asarray(t, dtype=np.float64).copy()
-    rows, offsets = [], [0]
-    i = 0
-    n = len(t)
-    for ut in update_times:
-        while i + 1 < n and t[i + 1] <= ut:
-            dt = t[i + 1] - t[i]
-            if dt >= 0:
-                rows.append((*w[i], *a[i], dt))
-            i += 1
-        dtf = ut - t[i]
-        if dtf > 0:
-            rows.append((*w[i], *a[i], dtf))
-            t[i] = ut
-        offsets.append(len(rows))
-    S = np.array(rows, dtype=np.float64).reshape(-1, 7)
-    return S, np.array(offsets, dtype=np.int64)
+    import ctypes
+    from . import capi
+    lib = capi.load()
+    t = np.ascontiguousarray(t, dtype=np.float64); w = np.ascontiguousarray(w, dtype=np.float64).reshape(-1, 3)
+    a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1, 3); ut = np.ascontiguousarray(update_times, dtype=np.float64)
+    off = np.zeros(len(ut) + 1, dtype=np.int64)
+    ne = ctypes.c_int64(0)
+    P = lambda x: ctypes.c_void_p(x.ctypes.data)
+    cap = len(t) + len(ut) + 1                     # every reading is fed at most once, plus one partial step per update
+    S = np.zeros((cap, 7))
+    nw = lib.cpi_cut_windows(len(t), P(t), P(w), P(a), len(ut), P(ut), int(imu_wait), cap, P(S), P(off), ctypes.byref(ne))
+    if nw < 0:
+        capi.check(int(nw))
+    return S[:ne.value].copy(), off[:nw + 1].copy()
 
 
 def make_states(records, lin, model, seed=SEED, perturb=True):

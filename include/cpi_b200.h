@@ -153,6 +153,23 @@ int cpi_predict_state_batch(int model, int64_t n, const double* states_k, const 
 /* JPLNavState::retract (JPLNavState.cpp:37-71): states_out[i] = states[i] (+) xi[i], xi = 15 doubles each. */
 int cpi_retract_batch(int64_t n, const double* states, const double* xi, double* states_out, void* stream);
 
+/* ---- window builder (host) ------------------------------------------------------------------------------------------------------ */
+
+/*
+ * Cut one IMU stream into the windows the reference preintegrates, one per update (camera) time: the loop of
+ * GraphSolver::createimufactor_cpi_v1/_v2 (solvers/GraphSolver_IMU.cpp:50-69, 105-124) incl. the partial tail step and the
+ * rewrite of the front stamp, fed as SimulationLoader::execute_publishing delivers the messages (sim/SimulationLoader.cpp:214-290:
+ * the IMU reading first at equal stamps) and initialised as GraphSolver::trytoinitalize does (solvers/GraphSolver.cpp:264, 357: the
+ * first update that finds >= imu_wait queued readings emits no window and keeps only the newest reading; imu_wait = 0: no such phase).
+ *   t[n_imu] seconds (non-decreasing), w / a [n_imu * 3], update_times[n_updates] (non-decreasing) -- all HOST arrays
+ *   samples   HOST, capacity cap_entries entries of CPI_SAMPLE_DOUBLES (may be NULL to count only)
+ *   offsets   HOST int64[n_updates + 1]; window k is entries offsets[k] .. offsets[k+1]-1 (CSR layout of cpi_preintegrate_batch)
+ * Returns the number of windows (<= n_updates) or a negative CPI_E* code; *n_entries receives the number of entries.
+ */
+int64_t cpi_cut_windows(int64_t n_imu, const double* t, const double* w, const double* a,
+                        int64_t n_updates, const double* update_times, int64_t imu_wait,
+                        int64_t cap_entries, double* samples, int64_t* offsets, int64_t* n_entries);
+
 /* ---- multi-GPU: one process per GPU, window batches sharded over the ranks ------------------------------------------------ */
 
 /*

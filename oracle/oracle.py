@@ -145,5 +145,23 @@ class Reference(_Base):
     def available(cls) -> bool:
         return os.path.exists(cls.path)
 
+    def replay_run(self, model, t, w, a, cam_t, lin, sigmas, flags=0, imu_wait=0):
+        """ref_replay_run (oracle/ref_shim.cpp): the reference DRIVER over one dataset run with its own deque handling.
+        Returns (samples fed [total,7], offsets[nwin+1], records[nwin, rd])."""
+        f = self.lib.ref_replay_run
+        f.argtypes = [ctypes.c_int, ctypes.c_int64, _P, _P, _P, ctypes.c_int64, _P, ctypes.c_int64, _P, _P, ctypes.c_int, ctypes.c_int64, _P, _PI, _P]
+        f.restype = ctypes.c_int64
+        t = np.ascontiguousarray(t, dtype=np.float64); w = np.ascontiguousarray(w, dtype=np.float64); a = np.ascontiguousarray(a, dtype=np.float64)
+        cam_t = np.ascontiguousarray(cam_t, dtype=np.float64); lin = np.ascontiguousarray(lin, dtype=np.float64)
+        sig = np.ascontiguousarray(sigmas, dtype=np.float64)
+        rd = 290 if model == 1 else 308
+        cap = len(t) + len(cam_t) + 1
+        S = np.zeros((cap, 7)); off = np.zeros(len(cam_t) + 1, dtype=np.int64); rec = np.zeros((len(cam_t), rd))
+        assert lin.shape[0] >= len(cam_t)
+        nw = f(model, len(t), _d(t), _d(w), _d(a), len(cam_t), _d(cam_t), int(imu_wait), _d(lin), _d(sig), flags, cap, _d(S), _i(off), _d(rec))
+        if nw < 0:
+            raise RuntimeError("ref_replay_run failed")
+        return S[:off[nw]].copy(), off[:nw + 1].copy(), rec[:nw].copy()
+
     def hardware_threads(self) -> int:
         return int(self.lib.ref_hardware_threads())

@@ -8,6 +8,8 @@
 //
 // The driving loop mirrors GraphSolver::createimufactor_cpi_v1/_v2 (solvers/GraphSolver_IMU.cpp:43-75, 97-130):
 // construct, setLinearizationPoints, feed_IMU per step, read the public fields.
+#include <deque>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include <cstdint>
@@ -166,5 +168,96 @@ void ref_quat_multiply(const double* q, const double* p, double* out) {
 void ref_Exp(const double* w, double* R_colmajor) { M3 r = Exp(V3(w[0], w[1], w[2])); put3x3(R_colmajor, r); }
 
 int ref_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
+
+// Replay of the reference DRIVER over one dataset run, with std::deque containers handled exactly as the reference handles them:
+//   GraphSolver::addmeasurement_imu (solvers/GraphSolver.cpp:58-69): push_back as readings arrive;
+//   SimulationLoader::execute_publishing (sim/SimulationLoader.cpp:214-290): at equal stamps the IMU reading is delivered before the camera;
+//   GraphSolver::addmeasurement_uv (solvers/GraphSolver.cpp:85-119): size() < 2 -> return; not initialised -> trytoinitalize;
+//   GraphSolver::trytoinitalize (solvers/GraphSolver.cpp:264, 357): needs >= imuWait queued readings, then erase(begin, end-1);
+//   GraphSolver::createimufactor_cpi_v1/_v2 (solvers/GraphSolver_IMU.cpp:43-75, 97-130): the two loops below, on the reference's
+//   own CpiV1 / CpiV2 objects, fed with the reference's own arguments (t_0, t_1, w_0, a_0, w_1, a_1).
+// The vision half of the solver cannot be built here (GTSAM), so the linearisation points -- which the reference takes from its state
+// estimate -- are an input (lin, one per camera frame); preintegration does not depend on where they came from.
+// Outputs: the entries the reference fed, in the CSR layout of include/cpi_b200.h (what cpi_cut_windows must reproduce bit for bit),
+// and the reference's records for them.  Returns the number of windows, or -1 if out_samples is too small.
+int64_t ref_replay_run(int model, int64_t n_imu, const double* t, const double* w, const double* a, int64_t n_cam, const double* cam_t,
+                       int64_t imu_wait, const double* lin, const double* sig, int flags, int64_t cap_entries, double* out_samples,
+                       int64_t* out_offsets, double* out_records) {
+    if (model != 1 && model != 2) return -1;
+    const int rd = model == 1 ? CPI_REC_V1_DOUBLES : CPI_REC_V2_DOUBLES;
+    std::deque<double> imu_times;
+    std::deque<V3, Eigen::aligned_allocator<V3> > imu_linaccs, imu_angvel;
+    bool systeminitalized = imu_wait == 0;
+    int64_t next_imu = 0, nwin = 0, ne = 0;
+    out_offsets[0] = 0;
+    bool overflow = false;
+    auto record = [&](double t0, double t1, const V3& w0, const V3& a0) {
+        if (ne < cap_entries) {
+            double* s = out_samples + ne * CPI_SAMPLE_DOUBLES;
+            s[0] = w0(0); s[1] = w0(1); s[2] = w0(2); s[3] = a0(0); s[4] = a0(1); s[5] = a0(2); s[6] = t1 - t0;   // feed_IMU: delta_t = t_1 - t_0
+        } else overflow = true;
+        ne++;
+    };
+    for (int64_t c = 0; c < n_cam; c++) {
+        const double updatetime = cam_t[c];
+        while (next_imu < n_imu && t[next_imu] <= updatetime) {                  // addmeasurement_imu, IMU first at equal stamps
+            imu_times.push_back(t[next_imu]);
+            imu_linaccs.push_back(V3(a[3 * next_imu], a[3 * next_imu + 1], a[3 * next_imu + 2]));
+            imu_angvel.push_back(V3(w[3 * next_imu], w[3 * next_imu + 1], w[3 * next_imu + 2]));
+            next_imu++;
+        }
+        if (imu_times.size() < 2) continue;                                       // GraphSolver.cpp:85
+        if (!systeminitalized) {                                                  // GraphSolver.cpp:264, 357
+            if (imu_times.size() < (size_t)imu_wait) continue;
+            imu_times.erase(imu_times.begin(), imu_times.end() - 1);
+            imu_linaccs.erase(imu_linaccs.begin(), imu_linaccs.end() - 1);
+            imu_angvel.erase(imu_angvel.begin(), imu_angvel.end() - 1);
+            systeminitalized = true;
+            continue;
+        }
+        const double* l = lin + nwin * CPI_LIN_DOUBLES;
+        V3 bw(l[0], l[1], l[2]), ba(l[3], l[4], l[5]), g(l[10], l[11], l[12]);
+        V4 q(l[6], l[7], l[8], l[9]);
+        double* rec = out_records + nwin * (int64_t)rd;
+        // GraphSolver_IMU.cpp:43-75 (model 1) / 97-130 (model 2): same statements, same containers
+#define CPI_REPLAY_LOOP(cpi)                                                                                                              \
+        while (imu_times.size() > 1 && imu_times.at(1) <= updatetime) {                                                                    \
+            double dt = imu_times.at(1) - imu_times.at(0);                                                                                 \
+            if (dt >= 0) {                                                                                                                 \
+                cpi.feed_IMU(imu_times.at(0), imu_times.at(1), imu_angvel.at(0), imu_linaccs.at(0), imu_angvel.at(1), imu_linaccs.at(1)); \
+                record(imu_times.at(0), imu_times.at(1), imu_angvel.at(0), imu_linaccs.at(0));                                            \
+            }                                                                                                                              \
+            imu_angvel.erase(imu_angvel.begin());                                                                                          \
+            imu_linaccs.erase(imu_linaccs.begin());                                                                                        \
+            imu_times.erase(imu_times.begin());                                                                                            \
+        }                                                                                                                                  \
+        double dt_f = updatetime - imu_times.at(0);                                                                                        \
+        if (dt_f > 0) {                                                                                                                    \
+            cpi.feed_IMU(imu_times.at(0), updatetime, imu_angvel.at(0), imu_linaccs.at(0), imu_angvel.at(0), imu_linaccs.at(0));          \
+            record(imu_times.at(0), updatetime, imu_angvel.at(0), imu_linaccs.at(0));                                                     \
+            imu_times.at(0) = updatetime;                                                                                                  \
+        }
+        if (model == 1) {
+            CpiV1 cpi(sig[0], sig[1], sig[2], sig[3]);
+            cpi.q_k2tau << 0, 0, 0, 1;
+            cpi.setLinearizationPoints(bw, ba, q, g);
+            cpi.imu_avg = false;
+            CPI_REPLAY_LOOP(cpi)
+            fill_common(cpi, rec);
+        } else {
+            CpiV2 cpi(sig[0], sig[1], sig[2], sig[3]);
+            cpi.q_k2tau << 0, 0, 0, 1;
+            cpi.setLinearizationPoints(bw, ba, q, g);
+            cpi.imu_avg = false;
+            cpi.state_transition_jacobians = (flags & CPI_FLAG_ANALYTIC_JACOBIANS) == 0;     // GraphSolver_IMU.cpp:100 sets true
+            CPI_REPLAY_LOOP(cpi)
+            fill_common(cpi, rec);
+            put3x3(rec + CPI_REC_OA, cpi.O_a); put3x3(rec + CPI_REC_OB, cpi.O_b);
+        }
+#undef CPI_REPLAY_LOOP
+        out_offsets[++nwin] = ne;
+    }
+    return overflow ? -1 : nwin;
+}
 
 }  // extern "C"

@@ -58,8 +58,15 @@ def main():
     cam = np.array([float(l.split()[-1]) for l in open(f"{REF}/GAZEBO_FREQ_200/rawdata_00/camera_data_meas.dat")]) * 1e-3
     cam = cam[(cam > t[0]) & (cam < t[-1])]
     cam = np.concatenate([cam[:25], [cam[25] + 0.0023]])     # last update falls between IMU stamps: partial tail step
-    S, off = synth.cut_windows(t, w, a, cam)
-    cases["cam200"] = dict(samples=S, offsets=off, lin=rand_lin(rng, len(off) - 1), cam_times=cam)
+    # the windows are cut by the REFERENCE's own driver loop (oracle/ref_shim.cpp:ref_replay_run -- std::deque handling, feed_IMU
+    # arguments and erase order of GraphSolver_IMU.cpp:50-69), not by the product's cutter: cpi_cut_windows is tested against this
+    lin_cam = rand_lin(rng, len(cam))
+    S, off, _ = R.replay_run(1, t, w, a, cam, lin_cam, synth.SIGMAS, 0, imu_wait=0)
+    assert len(off) - 1 == len(cam)
+    cases["cam200"] = dict(samples=S, offsets=off, lin=lin_cam, cam_times=cam)
+    # a second cut of the same stream WITH the reference's initialisation phase (imuWait queued readings, GraphSolver.cpp:264, 357)
+    S_i, off_i, _ = R.replay_run(1, t, w, a, cam, lin_cam, synth.SIGMAS, 0, imu_wait=300)
+    extra_init = dict(samples=S_i, offsets=off_i)
 
     # ---- 2. long windows cut at stride from the real streams
     for rate, ns, nwin in ((200, 200, 8), (100, 100, 4), (400, 400, 4)):
@@ -114,6 +121,7 @@ def main():
                     out[f"{name}/offsets_avg"] = off
                 out[f"{name}/records_m{model}_f{flags}"] = R.preintegrate(model, S, c["lin"], synth.SIGMAS, flags, offsets=off)
     out["sigmas"] = synth.SIGMAS
+    out["cam200_init300/samples"] = extra_init["samples"]; out["cam200_init300/offsets"] = extra_init["offsets"]
     np.savez_compressed(os.path.join(HERE, "preint_golden.npz"), **out)
     print("preint cases:", {k: len(v["offsets"]) - 1 for k, v in cases.items()})
 

@@ -81,7 +81,10 @@ def test_synth_is_partition_independent():
 
 
 def test_cut_windows_replays_reference_driver(golden):
-    """cut_windows == the loop at GraphSolver_IMU.cpp:50-69 (incl. the partial tail step and the imu_times[0] rewrite)."""
+    """cpi_cut_windows (C ABI, host) == the reference's driver loop.  The golden cam200 windows were cut by the REFERENCE's loop itself
+    (oracle/ref_shim.cpp:ref_replay_run: std::deque handling, feed_IMU arguments and erase order of GraphSolver_IMU.cpp:50-69, message
+    order of SimulationLoader.cpp:214-290), not by the product: bit-for-bit, incl. the partial tail step, the imu_times[0] rewrite and
+    the initialisation phase that drops the first imuWait readings (GraphSolver.cpp:264, 357)."""
     G = golden["preint"]
     t, w, a = synth.parse_imu_dat(os.path.join(ROOT, "tests", "golden", "imu_200hz_run00_head.dat"))
     S, off = synth.cut_windows(t, w, a, G["cam200/cam_times"])
@@ -90,6 +93,13 @@ def test_cut_windows_replays_reference_driver(golden):
     cam = G["cam200/cam_times"]
     assert np.allclose(dts[1:], np.diff(cam), atol=1e-9)        # every window spans exactly camera-to-camera
     assert abs(S[off[-2]:off[-1], 6][-1] - 0.0023) < 1e-9       # the last window ends with a partial step
+    Si, offi = synth.cut_windows(t, w, a, cam, imu_wait=300)
+    assert np.array_equal(offi, G["cam200_init300/offsets"]) and np.array_equal(Si, G["cam200_init300/samples"]) and 0 < len(offi) < len(off)
+    # error behaviour: unsorted stamps are rejected
+    import pytest as _pt
+    from cpi_b200.capi import CpiError
+    with _pt.raises(CpiError):
+        synth.cut_windows(t[::-1], w, a, cam)
 
 
 def test_preint_staging_layout():
