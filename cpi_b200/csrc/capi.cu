@@ -289,6 +289,49 @@ int cpi_imu_factor_hessian_batch(int model, int64_t n_factors, const double* rec
     return CPI_OK;
 }
 
+int cpi_imu_factor_whiten_batch(int model, int64_t n_factors, const double* records, const double* e, const double* H1, const double* H2,
+                                double* A1, double* A2, double* b, void* stream) {
+    if (model != 1 && model != 2) return fail(CPI_EINVAL, "model must be 1 or 2 (got %d)", model);
+    if (n_factors < 0) return fail(CPI_EINVAL, "negative count");
+    if (n_factors == 0) return CPI_OK;
+    if (!records || !e || !H1 || !H2 || !A1 || !A2 || !b) return fail(CPI_EINVAL, "null pointer argument");
+    DevInfo d;
+    int rc = device_info(d);
+    if (rc) return rc;
+    CU(cpi::whiten_launch(cpi_record_doubles(model), n_factors, records, e, H1, H2, A1, A2, b, (cudaStream_t)stream));
+    g_launches += 1;
+    return CPI_OK;
+}
+
+int cpi_imu_chain_assemble(int64_t n_factors, const double* G11, const double* G12, const double* G22, const double* g1, const double* g2, double lambda,
+                           const double* prior_info0, const double* prior_rhs0, double* D, double* E, double* rhs, void* stream) {
+    if (n_factors < 0) return fail(CPI_EINVAL, "negative count");
+    if (n_factors > 0 && (!G11 || !G12 || !G22 || !g1 || !g2 || !E)) return fail(CPI_EINVAL, "null pointer argument");
+    if (!D || !rhs) return fail(CPI_EINVAL, "null pointer argument");
+    if (n_factors >= 2147483647) return fail(CPI_EINVAL, "chain too long");
+    DevInfo d;
+    int rc = device_info(d);
+    if (rc) return rc;
+    CU(cpi::chain_assemble_launch(n_factors, G11, G12, G22, g1, g2, lambda, prior_info0, prior_rhs0, D, E, rhs, (cudaStream_t)stream));
+    g_launches += 1;
+    return CPI_OK;
+}
+
+int64_t cpi_imu_chain_solve_workspace(int64_t n_states) { return n_states < 0 ? (int64_t)CPI_EINVAL : cpi::chain_solve_workspace_bytes(n_states); }
+
+int cpi_imu_chain_solve(int64_t n_states, const double* D, const double* E, const double* rhs, double* x, void* workspace, void* stream) {
+    if (n_states < 0) return fail(CPI_EINVAL, "negative count");
+    if (n_states == 0) return CPI_OK;
+    if (!D || !rhs || !x || (n_states > 1 && (!E || !workspace))) return fail(CPI_EINVAL, "null pointer argument");
+    DevInfo d;
+    int rc = device_info(d);
+    if (rc) return rc;
+    int launches = 0;
+    CU(cpi::chain_solve_launch(n_states, D, E, rhs, x, (double*)workspace, (cudaStream_t)stream, &launches));
+    g_launches += launches;
+    return CPI_OK;
+}
+
 int cpi_predict_state_batch(int model, int64_t n, const double* states_k, const double* records, const double* lin, double* states_k1, void* stream) {
     if (model != 1 && model != 2) return fail(CPI_EINVAL, "model must be 1 or 2 (got %d)", model);
     if (n < 0) return fail(CPI_EINVAL, "negative count");

@@ -92,6 +92,78 @@ def factor_hessian(model, records, e, H1, H2, stream=None):
     return tuple(t.cpu().numpy() for t in out) if host else out
 
 
+def factor_whiten(model, records, e, H1, H2, stream=None):
+    """Explicitly whitened form (cpi_imu_factor_whiten_batch): A1 = R_w H1, A2 = R_w H2 [n,225 col-major], b = -R_w e [n,15], with
+    R_w the upper Cholesky factor of P_meas^-1 (GTSAM's Gaussian::Covariance).  Device tensors in/out, or numpy.  Parity unpinned."""
+    import torch
+
+    lib = capi.load()
+    host = isinstance(records, np.ndarray)
+    if host:
+        records, e, H1, H2 = (torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda() for a in (records, e, H1, H2))
+    n = records.numel() // REC_DOUBLES[model]
+    A1, A2 = (torch.empty((n, 225), dtype=torch.float64, device=records.device) for _ in range(2))
+    b = torch.empty((n, 15), dtype=torch.float64, device=records.device)
+    st = stream if stream is not None else torch.cuda.current_stream()
+    capi.check(lib.cpi_imu_factor_whiten_batch(model, n, _tptr(records.contiguous()), _tptr(e.contiguous()), _tptr(H1.contiguous()), _tptr(H2.contiguous()),
+                                               _tptr(A1), _tptr(A2), _tptr(b), ctypes.c_void_p(st.cuda_stream)))
+    out = (A1, A2, b)
+    return tuple(t.cpu().numpy() for t in out) if host else out
+
+
+def chain_assemble(G11, G12, G22, g1, g2, lam=0.0, prior_info0=None, prior_rhs0=None, stream=None):
+    """Block-tridiagonal normal equations of the chain x_0 .. x_n from the per-factor information blocks (cpi_imu_chain_assemble).
+    Device tensors.  Returns (D [n+1,225], E [n,225], rhs [n+1,15])."""
+    import torch
+
+    lib = capi.load()
+    n = G11.shape[0]
+    dev = G11.device
+    D = torch.empty((n + 1, 225), dtype=torch.float64, device=dev)
+    E = torch.empty((max(n, 1), 225), dtype=torch.float64, device=dev)
+    rhs = torch.empty((n + 1, 15), dtype=torch.float64, device=dev)
+    st = stream if stream is not None else torch.cuda.current_stream()
+    capi.check(lib.cpi_imu_chain_assemble(n, _tptr(G11), _tptr(G12), _tptr(G22), _tptr(g1), _tptr(g2), float(lam), _tptr(prior_info0), _tptr(prior_rhs0),
+                                          _tptr(D), _tptr(E), _tptr(rhs), ctypes.c_void_p(st.cuda_stream)))
+    return D, E[:n], rhs
+
+
+def chain_solve(D, E, rhs, stream=None, workspace=None):
+    """x = A^-1 rhs for the SPD block-tridiagonal A = tridiag(E^T, D, E) by block cyclic reduction on the device (cpi_imu_chain_solve)."""
+    import torch
+
+    lib = capi.load()
+    n = D.shape[0]
+    x = torch.empty((n, 15), dtype=torch.float64, device=D.device)
+    nbytes = int(lib.cpi_imu_chain_solve_workspace(n))
+    if workspace is None or workspace.numel() * 8 < nbytes:
+        workspace = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=D.device)
+    st = stream if stream is not None else torch.cuda.current_stream()
+    capi.check(lib.cpi_imu_chain_solve(n, _tptr(D), _tptr(E), _tptr(rhs), _tptr(x), _tptr(workspace), ctypes.c_void_p(st.cuda_stream)))
+    return x
+
+
+_PRIOR = {}
+
+
+def chain_lm_step(model, states, records, lin, lam=0.0, prior_sigma=1e-4, stream=None):
+    """One damped Gauss-Newton (Levenberg-Marquardt) step of an IMU-only chain, entirely on the device:
+    evaluateError for every factor -> information blocks -> block-tridiagonal assembly (prior 1/prior_sigma^2 on x_0: the
+    reference initialises with cov = 1e-8 I, GraphSolver.cpp:331) -> block-cyclic-reduction solve -> JPLNavState::retract.
+    Returns (new_states, delta, cost = sum e^T P^-1 e before the step)."""
+    import torch
+
+    dev = states.device
+    key = (dev, prior_sigma)
+    if key not in _PRIOR:
+        _PRIOR[key] = (torch.eye(15, dtype=torch.float64, device=dev) / (prior_sigma * prior_sigma)).reshape(-1).contiguous()
+    e, H1, H2 = factor_eval(model, states, records, lin, stream=stream)
+    G11, G12, G22, g1, g2, f = factor_hessian(model, records, e, H1, H2, stream=stream)
+    D, E, rhs = chain_assemble(G11, G12, G22, g1, g2, lam, _PRIOR[key], None, stream=stream)
+    dx = chain_solve(D, E, rhs, stream=stream)
+    return retract(states, dx, stream=stream), dx, f.sum()
+
+
 def predict_state(model, states_k, records, lin, stream=None):
     """getpredictedstate_v1/_v2 (solvers/GraphSolver_IMU.cpp:263-307), batched.  Device tensors, or numpy (staged via torch)."""
     import torch

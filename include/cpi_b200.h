@@ -143,6 +143,34 @@ int cpi_imu_factor_hessian_batch(int model, int64_t n_factors, const double* rec
                                  const double* e, const double* H1, const double* H2,
                                  double* G11, double* G12, double* G22, double* g1, double* g2, double* f, void* stream);
 
+/*
+ * The explicitly whitened Jacobian form GTSAM's NoiseModelFactor::linearize produces with Gaussian::Covariance(P_meas):
+ *     A1 = R_w H1,  A2 = R_w H2  (15x15 column-major each),  b = -R_w e  (15),   R_w = upper Cholesky factor of P_meas^-1.
+ * PARITY UNPINNED (GTSAM is not in the reference tree); validated against numpy: A^T A = H^T P^-1 H, R_w upper triangular.
+ */
+int cpi_imu_factor_whiten_batch(int model, int64_t n_factors, const double* records,
+                                const double* e, const double* H1, const double* H2,
+                                double* A1, double* A2, double* b, void* stream);
+
+/*
+ * IMU-only chain x_0 - x_1 - ... - x_n (factor f links states f and f+1): what the smoother assembles and solves after the
+ * linearisation (solvers/GraphSolver.cpp:202-203), on the device.
+ *   cpi_imu_chain_assemble   scatter-add of the blocks of cpi_imu_factor_hessian_batch into the block-tridiagonal normal equations:
+ *       D[k] (n+1 blocks 15x15) = G22[k-1] + G11[k] + lambda I (+ prior_info0 on x_0),  E[k] (n blocks, block (k,k+1)) = G12[k],
+ *       rhs[k] (15) = g2[k-1] + g1[k] (+ prior_rhs0).  prior_* may be NULL; lambda = Levenberg damping.
+ *   cpi_imu_chain_solve      x = (that SPD block-tridiagonal matrix)^-1 rhs by block cyclic reduction (Cholesky on the 15x15 pivots):
+ *       ~2 log2(n) + 1 kernel launches instead of an n-step sequential block recurrence.  `workspace`: device buffer of
+ *       cpi_imu_chain_solve_workspace(n_states) bytes.  The step is then applied with cpi_retract_batch.
+ * All pointers are DEVICE pointers.  PARITY UNPINNED; validated against banded / dense CPU solves of the same system.
+ */
+int cpi_imu_chain_assemble(int64_t n_factors, const double* G11, const double* G12, const double* G22,
+                           const double* g1, const double* g2, double lambda,
+                           const double* prior_info0, const double* prior_rhs0,
+                           double* D, double* E, double* rhs, void* stream);
+int64_t cpi_imu_chain_solve_workspace(int64_t n_states);
+int cpi_imu_chain_solve(int64_t n_states, const double* D, const double* E, const double* rhs,
+                        double* x, void* workspace, void* stream);
+
 /* ---- callers either side of the factor ("next" rows) ----------------------------------------------------------------- */
 
 /* x_{k+1} prediction from x_k and a record: getpredictedstate_v1/_v2 (GraphSolver_IMU.cpp:263-307).

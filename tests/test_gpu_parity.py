@@ -367,3 +367,107 @@ def test_multiwave_capacity_path(cuda, oracle, model, dtype, n, ns):
     # host entry point (chunk-pipelined) gives the same bits
     host = preint.preintegrate_host(model, Sx, Lx, synth.SIGMAS, 0, ns=ns)
     assert np.array_equal(host, got)
+
+
+@pytest.mark.parametrize("model", [1, 2])
+def test_whitened_form_against_numpy(cuda, model):
+    """A = R_w [H1 H2], b = -R_w e with R_w = chol_upper(P^-1) (GTSAM's Gaussian::Covariance; PARITY UNPINNED, GTSAM is not in the tree)."""
+    from cpi_b200 import preint, factor
+    n = 200
+    S, L = synth.make_windows(n, 60, rate=200.0, first_window=4711, special=False)
+    rec = preint.preintegrate_host(model, S, L, synth.SIGMAS, 0, ns=60)
+    X = synth.make_states(rec, L, model)
+    e, H1, H2 = factor.factor_eval_host(model, X, rec, L)
+    A1, A2, b = factor.factor_whiten(model, rec, e, H1, H2)
+    G11, G12, G22, g1, g2, f = factor.factor_hessian(model, rec, e, H1, H2)
+    worst = 0.0
+    for i in range(n):
+        a1 = A1[i].reshape(15, 15, order="F"); a2 = A2[i].reshape(15, 15, order="F")
+        # (1) the whitened blocks reproduce the information form exactly up to rounding
+        for got, ref in ((a1.T @ a1, G11[i].reshape(15, 15, order="F")), (a1.T @ a2, G12[i].reshape(15, 15, order="F")), (a2.T @ a2, G22[i].reshape(15, 15, order="F")),
+                         (a1.T @ b[i], g1[i]), (a2.T @ b[i], g2[i]), (b[i] @ b[i], f[i])):
+            worst = max(worst, np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300))
+        # (2) R_w = A1 H1^-1 is upper triangular with positive diagonal and R_w^T R_w P = I   (Jacobi-scaled: cond(P) ~ 1e7)
+        P = rec[i, 65:290].reshape(15, 15, order="F"); d = 1.0 / np.sqrt(np.diag(P))
+        Rw = np.linalg.solve(H1[i].reshape(15, 15, order="F").T, a1.T).T if np.linalg.cond(H1[i].reshape(15, 15, order="F")) < 1e8 else None
+        if Rw is not None:
+            assert np.max(np.abs(np.tril(Rw, -1))) <= 1e-6 * np.max(np.abs(Rw)) and np.all(np.diag(Rw) > 0)
+            Is = (Rw / d[None, :]).T @ (Rw / d[None, :]) @ (P * d[:, None] * d[None, :])
+            assert np.max(np.abs(Is - np.eye(15))) < 1e-6
+    print("worst relative mismatch whitened vs information form", worst)
+    assert worst <= 1e-9
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 64, 300, 4999])
+def test_chain_assemble_and_block_cyclic_reduction_solve(cuda, n):
+    """IMU-only chain of n factors: device assembly of the block-tridiagonal normal equations + block-cyclic-reduction solve, against a
+    CPU banded Cholesky (scipy.linalg.solveh_banded) of the same system.  PARITY UNPINNED (the reference hands this to GTSAM's smoother,
+    GraphSolver.cpp:202-203); odd / even / power-of-two chain lengths exercise every end case of the reduction."""
+    import scipy.linalg
+    from cpi_b200 import preint, factor
+    torch = cuda
+    model = 1
+    S, L = synth.make_windows(n, 20, rate=200.0, first_window=9000, special=False)
+    rec = preint.preintegrate_host(model, S, L, synth.SIGMAS, 0, ns=20)
+    X = synth.make_states(rec, L, model)
+    dX, dR, dL = (torch.from_numpy(a).cuda() for a in (X, rec, L))
+    e, H1, H2 = factor.factor_eval(model, dX, dR, dL)
+    G11, G12, G22, g1, g2, f = factor.factor_hessian(model, dR, e, H1, H2)
+    prior = (torch.eye(15, dtype=torch.float64, device="cuda") * 1e8).reshape(-1).contiguous()
+    D, E, rhs = factor.chain_assemble(G11, G12, G22, g1, g2, 1e-3, prior, None)
+    x = factor.chain_solve(D, E, rhs)
+    torch.cuda.synchronize()
+    Dh, Eh, bh, xh = D.cpu().numpy(), E.cpu().numpy(), rhs.cpu().numpy(), x.cpu().numpy()
+    # assembly against numpy
+    G11h, G12h, G22h, g1h, g2h = (t.cpu().numpy() for t in (G11, G12, G22, g1, g2))
+    Dref = np.zeros((n + 1, 225)); Dref[:n] += G11h; Dref[1:] += G22h; Dref[:, ::16] += 1e-3; Dref[0, ::16] += 1e8
+    bref = np.zeros((n + 1, 15)); bref[:n] += g1h; bref[1:] += g2h
+    assert np.array_equal(Eh, G12h) and np.allclose(Dh, Dref, rtol=1e-15, atol=0) and np.allclose(bh, bref, rtol=1e-15, atol=0)
+    # banded reference solve (lower form, bandwidth 29), Jacobi-scaled like any sane CPU solve of this badly scaled system
+    N = 15 * (n + 1)
+    sc = 1.0 / np.sqrt(np.concatenate([Dh[k].reshape(15, 15, order="F").diagonal() for k in range(n + 1)]))
+    ab = np.zeros((30, N))
+    for k in range(n + 1):
+        Dk = Dh[k].reshape(15, 15, order="F")
+        for c in range(15):
+            col = 15 * k + c
+            ab[0:15 - c, col] = Dk[c:, c]
+            if k < n:
+                Ek = Eh[k].reshape(15, 15, order="F")          # block (k, k+1): rows 15k.., cols 15(k+1)..; lower part holds E^T at rows 15(k+1).., col 15k+c
+                ab[15 - c:30 - c, col] = Ek[c, :]
+    for col in range(N):
+        m = min(30, N - col)
+        ab[:m, col] *= sc[col] * sc[col:col + m]
+    xr = scipy.linalg.solveh_banded(ab, bh.reshape(-1) * sc, lower=True) * sc
+    err = np.linalg.norm(xh.reshape(-1) - xr) / np.linalg.norm(xr)
+    # residual of the device solution in the original system
+    r = np.zeros((n + 1, 15))
+    for k in range(n + 1):
+        r[k] = Dh[k].reshape(15, 15, order="F") @ xh[k] - bh[k]
+        if k < n:
+            Ek = Eh[k].reshape(15, 15, order="F")
+            r[k] += Ek @ xh[k + 1]; r[k + 1] += Ek.T @ xh[k]
+    res = np.linalg.norm(r) / np.linalg.norm(bh)
+    print(n, "rel err vs banded CPU solve", err, "relative residual", res)
+    assert err <= 1e-7 and res <= 1e-9
+
+
+def test_chain_lm_step_reduces_the_cost(cuda):
+    """eval -> Hessian blocks -> assemble -> solve -> retract, all on device: a Gauss-Newton step on a perturbed 5k-keyframe chain must
+    reduce sum e^T P^-1 e by orders of magnitude (the chain started from the exact prediction has zero residual)."""
+    from cpi_b200 import preint, factor
+    torch = cuda
+    n = 4999
+    S, L = synth.make_windows(n, 20, rate=200.0, first_window=9000, special=False)
+    rec = preint.preintegrate_host(1, S, L, synth.SIGMAS, 0, ns=20)
+    X = synth.make_states(rec, L, 1, perturb=False)
+    rng = np.random.default_rng(3)
+    Xp = X.copy(); Xp[1:, 7:10] += rng.normal(0, 1e-3, (n, 3)); Xp[1:, 13:16] += rng.normal(0, 1e-3, (n, 3)); Xp[1:, 4:7] += rng.normal(0, 1e-5, (n, 3))
+    dX, dR, dL = (torch.from_numpy(a).cuda() for a in (Xp, rec, L))
+    X1, dx, c0 = factor.chain_lm_step(1, dX, dR, dL)
+    X2, dx2, c1 = factor.chain_lm_step(1, X1, dR, dL)
+    X3, dx3, c2 = factor.chain_lm_step(1, X2, dR, dL)
+    torch.cuda.synchronize()
+    c0, c1, c2 = float(c0), float(c1), float(c2)
+    print("cost", c0, c1, c2, "|dx|", float(dx.norm()), float(dx2.norm()), float(dx3.norm()))
+    assert np.isfinite(c0) and c1 < 1e-3 * c0 and c2 <= c1 * 1.0001 and torch.all(torch.isfinite(X3))
