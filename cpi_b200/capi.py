@@ -29,6 +29,8 @@ SYMBOLS = {
     "cpi_imu_chain_solve": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cpi_predict_state_batch": (c_int, [c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cpi_retract_batch": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "cpi_host_register": (c_int, [c_vp, ctypes.c_size_t]),
+    "cpi_host_unregister": (c_int, [c_vp]),
     "cpi_cut_windows": (c_i64, [c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "cpi_comm_unique_id": (c_int, [c_vp]),
     "cpi_comm_create": (c_int, [c_vp, c_int, c_int, ctypes.POINTER(c_vp)]),

@@ -179,45 +179,76 @@ int cpi_preintegrate_batch_host(int model, int dtype, int64_t n_windows, const i
     if ((rc = dev_buf(2, (size_t)n_windows * rd * es, &d_o))) return rc;
     if (sample_offsets && (rc = dev_buf(3, (size_t)(n_windows + 1) * 8, &d_off))) return rc;
 
-    // Chunked pipeline: H2D of chunk k+1 runs under the kernel of chunk k, D2H of chunk k under the kernel of chunk k+1.
-    // The kernel is latency-bound on small grids, so every chunk is launched with the windows-per-block the
-    // WHOLE batch would use: a chunk then occupies only its share of the SMs and the chunk kernels run concurrently on
-    // separate streams instead of serialising.
+    // Chunked pipeline: H2D of chunk k+1 runs under the kernel of chunk k, D2H of chunk k under the kernel of chunk k+1.  The
+    // default kernels are one-warp CTAs, so chunk kernels of different streams co-reside on the SMs and a batch can be cut into
+    // many small chunks: the tail after the last H2D is then one SMALL kernel (few warps per SM run the 200-sample chain faster
+    // than a full SM) plus a small D2H.  The lane-per-window kernels (imu_avg / analytic modes) are launched with the windows-per-
+    // block the WHOLE batch would use, so that a chunk occupies only its share of the SMs.
     const size_t in_bytes = (size_t)entries * CPI_SAMPLE_DOUBLES * es;
-    int nchunk = 1;
-    if (in_bytes >= ((size_t)24 << 20) && n_windows >= 8 * (int64_t)d.sms) nchunk = Scratch::NSTREAM;
-    if (const char* e = getenv("CPI_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= Scratch::NSTREAM) nchunk = v; }   // A/B measurements
     const int cap = cpi::preint_cap(model, dtype, flags, d.sms);     // windows per CTA of the kernel preint_launch will select
+    const bool small_ctas = cap <= 16;
+    int nchunk = 1;
+    if (in_bytes >= ((size_t)16 << 20) && n_windows >= 8 * (int64_t)d.sms) {
+        nchunk = small_ctas ? (int)(in_bytes >> 23) : Scratch::NSTREAM;          // ~8 MB of samples per chunk
+        if (nchunk < Scratch::NSTREAM) nchunk = Scratch::NSTREAM;
+        if (nchunk > 16) nchunk = 16;
+    }
+    if (const char* e = getenv("CPI_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 64) nchunk = v; }   // A/B measurements
     int64_t need = (n_windows + d.sms - 1) / d.sms;
     const int wpb = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
     const int64_t blocks = (n_windows + wpb - 1) / wpb;
     const int64_t blocks_per_chunk = (blocks + nchunk - 1) / nchunk;
 
     cudaStream_t s_in = g_scratch.stream;
-    if (sample_offsets) CU(cudaMemcpyAsync(d_off, sample_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, s_in));
+    rc = CPI_OK;
+    // every error path drains the streams before returning: async copies into the caller's buffers must not outlive the call
+#define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(CPI_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); goto drain; } } while (0)
+    if (sample_offsets) CUX(cudaMemcpyAsync(d_off, sample_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, s_in));
     for (int k = 0; k < nchunk; k++) {
         const int64_t lo = (int64_t)k * blocks_per_chunk * wpb;
         if (lo >= n_windows) break;
         const int64_t hi = (lo + blocks_per_chunk * wpb < n_windows) ? lo + blocks_per_chunk * wpb : n_windows;
         const int64_t e_lo = sample_offsets ? sample_offsets[lo] : lo * ent_w, e_hi = sample_offsets ? sample_offsets[hi] : hi * ent_w;
-        cudaStream_t sk = g_scratch.work[k];
-        CU(cudaMemcpyAsync((char*)d_l + (size_t)lo * CPI_LIN_DOUBLES * es, (const char*)lin + (size_t)lo * CPI_LIN_DOUBLES * es,
-                           (size_t)(hi - lo) * CPI_LIN_DOUBLES * es, cudaMemcpyHostToDevice, s_in));
+        const int si = k % Scratch::NSTREAM;
+        cudaStream_t sk = g_scratch.work[si];
+        CUX(cudaMemcpyAsync((char*)d_l + (size_t)lo * CPI_LIN_DOUBLES * es, (const char*)lin + (size_t)lo * CPI_LIN_DOUBLES * es,
+                            (size_t)(hi - lo) * CPI_LIN_DOUBLES * es, cudaMemcpyHostToDevice, s_in));
         if (e_hi > e_lo)
-            CU(cudaMemcpyAsync((char*)d_s + (size_t)e_lo * CPI_SAMPLE_DOUBLES * es, (const char*)samples + (size_t)e_lo * CPI_SAMPLE_DOUBLES * es,
-                               (size_t)(e_hi - e_lo) * CPI_SAMPLE_DOUBLES * es, cudaMemcpyHostToDevice, s_in));
-        CU(cudaEventRecord(g_scratch.ev[k], s_in));
-        CU(cudaStreamWaitEvent(sk, g_scratch.ev[k], 0));
-        // offsets are absolute entry indices, so CSR chunks keep the global sample base; uniform chunks shift it
-        const void* s_base = sample_offsets ? d_s : (const void*)((const char*)d_s + (size_t)e_lo * CPI_SAMPLE_DOUBLES * es);
-        rc = preintegrate_dev(model, dtype, hi - lo, sample_offsets ? (const int64_t*)d_off + lo : nullptr, ns_uniform, s_base,
-                              (const char*)d_l + (size_t)lo * CPI_LIN_DOUBLES * es, sigmas, flags, (char*)d_o + (size_t)lo * rd * es, sk, wpb);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync((char*)out_records + (size_t)lo * rd * es, (const char*)d_o + (size_t)lo * rd * es, (size_t)(hi - lo) * rd * es,
-                           cudaMemcpyDeviceToHost, sk));
+            CUX(cudaMemcpyAsync((char*)d_s + (size_t)e_lo * CPI_SAMPLE_DOUBLES * es, (const char*)samples + (size_t)e_lo * CPI_SAMPLE_DOUBLES * es,
+                                (size_t)(e_hi - e_lo) * CPI_SAMPLE_DOUBLES * es, cudaMemcpyHostToDevice, s_in));
+        CUX(cudaEventRecord(g_scratch.ev[si], s_in));
+        CUX(cudaStreamWaitEvent(sk, g_scratch.ev[si], 0));
+        {
+            // offsets are absolute entry indices, so CSR chunks keep the global sample base; uniform chunks shift it
+            const void* s_base = sample_offsets ? d_s : (const void*)((const char*)d_s + (size_t)e_lo * CPI_SAMPLE_DOUBLES * es);
+            rc = preintegrate_dev(model, dtype, hi - lo, sample_offsets ? (const int64_t*)d_off + lo : nullptr, ns_uniform, s_base,
+                                  (const char*)d_l + (size_t)lo * CPI_LIN_DOUBLES * es, sigmas, flags, (char*)d_o + (size_t)lo * rd * es, sk, wpb);
+            if (rc) goto drain;
+        }
+        CUX(cudaMemcpyAsync((char*)out_records + (size_t)lo * rd * es, (const char*)d_o + (size_t)lo * rd * es, (size_t)(hi - lo) * rd * es,
+                            cudaMemcpyDeviceToHost, sk));
     }
-    for (int k = 0; k < nchunk; k++) CU(cudaStreamSynchronize(g_scratch.work[k]));
-    CU(cudaStreamSynchronize(s_in));
+drain:
+#undef CUX
+    for (int k = 0; k < Scratch::NSTREAM; k++) {
+        cudaError_t e_ = cudaStreamSynchronize(g_scratch.work[k]);
+        if (e_ != cudaSuccess && rc == CPI_OK) rc = fail(CPI_ECUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e_));
+    }
+    {
+        cudaError_t e_ = cudaStreamSynchronize(s_in);
+        if (e_ != cudaSuccess && rc == CPI_OK) rc = fail(CPI_ECUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e_));
+    }
+    return rc;
+}
+
+int cpi_host_register(void* ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return fail(CPI_EINVAL, "null pointer argument");
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return CPI_OK;
+}
+int cpi_host_unregister(void* ptr) {
+    if (!ptr) return fail(CPI_EINVAL, "null pointer argument");
+    CU(cudaHostUnregister(ptr));
     return CPI_OK;
 }
 
@@ -244,6 +275,11 @@ int cpi_imu_factor_eval_batch_host(int model, int64_t n_factors, int64_t n_state
     if (n_factors == 0) return CPI_OK;
     if (!states || !records || !lin || !e) return fail(CPI_EINVAL, "null pointer argument");
     if (!idx_i && n_states < n_factors + 1) return fail(CPI_EINVAL, "chain indexing needs n_states >= n_factors + 1");
+    if ((idx_i == nullptr) != (idx_j == nullptr)) return fail(CPI_EINVAL, "idx_i and idx_j must both be given or both be null");
+    if (idx_i)
+        for (int64_t f = 0; f < n_factors; f++)
+            if (idx_i[f] < 0 || idx_i[f] >= n_states || idx_j[f] < 0 || idx_j[f] >= n_states)
+                return fail(CPI_EINVAL, "factor %lld: state index out of range [0, %lld)", (long long)f, (long long)n_states);
     const int rd = cpi_record_doubles(model);
     std::lock_guard<std::mutex> lk(g_scratch_mu);
     int rc = scratch_prepare();

@@ -30,11 +30,13 @@
 namespace cpi {
 
 constexpr int TRI_WPW = 10;                 // windows per warp (lanes 30, 31 idle)
-// CTA size (compile-time: it is the stride of the lane-private shared-memory slots).  Model 2 in fp64 needs 60 + 32 slot doubles per
-// lane, which fits 227 KB at 224 threads (7 warps, 70 windows) only.
-template <int MODEL, class T> struct TriNT { static constexpr int NT = 256; };
-template <> struct TriNT<2, double> { static constexpr int NT = 224; };
-constexpr int TRI_NBUF = 4;                 // 128-byte chunk buffers per window (TMA ring)
+// CTA = ONE warp = ten windows.  Nothing in the kernel is shared between warps, so one-warp CTAs cost nothing and buy (a) even
+// distribution by the hardware block scheduler (10 000 windows = 1 000 CTAs over 148 SMs: 6 or 7 per SM, one wave), (b) kernels of
+// different streams co-residing on an SM, which is what lets the host entry point pipeline a batch in many small chunks, and (c) a
+// finer tail on multi-wave batches.  Up to 8 CTAs per SM: 255 registers x 32 lanes x 8 = the register file; shared memory per CTA is
+// kept under 220 KB / 8 (model 2 in fp64: 7 CTAs per SM).
+template <int MODEL, class T> struct TriNT { static constexpr int NT = 32; };
+constexpr int TRI_NBUF = 3;                 // 128-byte chunk buffers per window (TMA ring)
 constexpr int TRI_BUF_STRIDE = TRI_NBUF * 128 + 16;   // bytes of sample staging per window, + 16 B pad (bank spread; 16-B aligned for TMA)
 // doubles per window of pre-pass scalars: 3 samples x 16 (model 1: 15 used) or 3 x 10 (model 2: 9 used), padded to an odd stride (bank spread)
 template <int MODEL> struct TriSC { static constexpr int PER = (MODEL == 1) ? 16 : 10, STRIDE = 3 * PER + 1 + (MODEL == 1 ? 2 : 0); };
@@ -62,17 +64,29 @@ template <int MODEL, class T> struct TriSmem {
     static constexpr int NT = TriNT<MODEL, T>::NT;
     static constexpr int WPB = TRI_WPW * NT / 32;                     // window slots per CTA
     static constexpr size_t off_fs = (size_t)TriL<MODEL>::NSL * NT * sizeof(T);
+#ifdef CPI_TRI_PSMEM
+    static constexpr size_t off_sc = off_fs + (size_t)33 * NT * sizeof(T);
+#else
     static constexpr size_t off_sc = off_fs + (size_t)TriL<MODEL>::NFS * NT * 8;
+#endif
     // scalar sets: one slot per window + one dummy slot per warp for the two idle lanes
     static constexpr size_t off_buf = (off_sc + (size_t)(WPB + NT / 32) * TriSC<MODEL>::STRIDE * 8 + 127) / 128 * 128;
     static constexpr size_t off_bar = off_buf + (size_t)WPB * TRI_BUF_STRIDE;
     static constexpr size_t bytes = off_bar + (size_t)WPB * 8 * TRI_NBUF;
 };
-static_assert(TriSmem<1, double>::bytes <= 232448 && TriSmem<2, double>::bytes <= 232448 && TriSmem<1, float>::bytes <= 232448 &&
-              TriSmem<2, float>::bytes <= 232448, "tri-lane smem layout exceeds 227 KB");
+#ifndef CPI_TRI_PSMEM
+static_assert(TriSmem<1, double>::bytes <= 28160 - 1024 && TriSmem<1, float>::bytes <= 28160 - 1024 && TriSmem<2, float>::bytes <= 28160 - 1024,
+              "8 CTAs per SM need <= 220 KB / 8 of shared memory each (incl. 1 KB the system reserves per CTA)");
+static_assert(TriSmem<2, double>::bytes <= 32182 - 1024, "model 2 fp64: 7 CTAs per SM");
+#endif
 
 #define SLT(e) sl[(e) * NT]
+#ifdef CPI_TRI_PSMEM        // experiment: covariance state parked in lane-private smem between groups, front state in registers
+#define FST(e) fsr[e]
+#define PST(e) ps[(e) * NT]
+#else
 #define FST(e) fs[(e) * NT]
+#endif
 #define CN(s) ((s) < 2 ? hdt : dt)                       /* x_{s+2} = x_1 + CN(s) k_{s+1}:  dt/2, dt/2, dt   (CpiV1.h:312, 323, 344) */
 #define KSUM(ks, k, s) ((s) == 0 ? (k) : ((s) == 3 ? (ks) + (k) : fma(T(2), (k), (ks))))   /* ((k1 + 2 k2) + 2 k3) + k4  (CpiV1.h:352) */
 #ifdef CPI_TRI_NOFENCE
@@ -95,7 +109,7 @@ template <class T> struct TriP {
 // One RK4 step of the covariance (model 1: CpiV1.h:272-353).  w, ah: estimated readings; R, Rm, R1: old / mid / new
 // rotation (row-major, lane frame); pgg, paa: the scalar diagonal blocks P_bg,bg and P_ba,ba at the start of the step.
 template <int MODEL, int NT, class T>
-CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, const T* w, const T* ah, const T* gt, const T* R, const T* Rm, const T* R1, T pgg, T paa, T dt, T dt6,
+CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, T* ps, const T* w, const T* ah, const T* gt, const T* R, const T* Rm, const T* R1, T pgg, T paa, T dt, T dt6,
                           T q_w, T q_wb, T q_a, T q_ab, int nx, int pv) {
     const T hdt = dt * T(0.5);
     constexpr int NS = (MODEL == 1) ? 12 : 15;            // slot entries per stage
@@ -106,6 +120,10 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, const T* w, const T* ah, const T* g
     //     CP = P_c,p      (starts as TP):  CP' = CV                            [recomputed from CV's stage values]
     // and the v rows gain  C_s P_c,J  with  C_s = -R_s^T [g_tau x]  (CpiV2.h:335).
     {   // ---- group 1a: TG, TT, GV, TV, stage by stage (self-contained: needs only w, the rotations and a_hat)
+#ifdef CPI_TRI_PSMEM
+#pragma unroll
+        for (int e = 0; e < 3; e++) { P.TG[e] = PST(e); P.TT[e] = PST(3 + e); P.GV[e] = PST(6 + e); P.TV[e] = PST(9 + e); }
+#endif
         T xTG[3], xTT[3], xGV[3], xTV[3], xTC[3], xCV[3];
         T sTG[3], sTT[3], sGV[3], sTV[3];
         T G1s[3], G2s[3], tts[3];                             // model 2: TG(start) columns 1, 2 and TT(start) entries 11, 21, 22
@@ -188,10 +206,18 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, const T* w, const T* ah, const T* g
             P.TG[e] = fma(dt6, sTG[e], P.TG[e]); P.TT[e] = fma(dt6, sTT[e], P.TT[e]); P.GV[e] = fma(dt6, sGV[e], P.GV[e]);
             P.TV[e] = fma(dt6, sTV[e], P.TV[e]);
         }
+#ifdef CPI_TRI_PSMEM
+#pragma unroll
+        for (int e = 0; e < 3; e++) { PST(e) = P.TG[e]; PST(3 + e) = P.TT[e]; PST(6 + e) = P.GV[e]; PST(9 + e) = P.TV[e]; }
+#endif
     }
     CPI_FENCE();
     {   // ---- group 1b: AV, VV (need TV's stage values)
         T xAV[3], xVV[3], sAV[3], sVV[3];
+#ifdef CPI_TRI_PSMEM
+#pragma unroll
+        for (int e = 0; e < 3; e++) { P.AV[e] = PST(12 + e); P.VV[e] = PST(15 + e); }
+#endif
 #pragma unroll
         for (int e = 0; e < 3; e++) { xAV[e] = P.AV[e]; xVV[e] = P.VV[e]; }
 #pragma unroll
@@ -232,11 +258,19 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, const T* w, const T* ah, const T* g
         }
 #pragma unroll
         for (int e = 0; e < 3; e++) { P.AV[e] = fma(dt6, sAV[e], P.AV[e]); P.VV[e] = fma(dt6, sVV[e], P.VV[e]); }
+#ifdef CPI_TRI_PSMEM
+#pragma unroll
+        for (int e = 0; e < 3; e++) { PST(12 + e) = P.AV[e]; PST(15 + e) = P.VV[e]; }
+#endif
     }
     CPI_FENCE();
     {   // ---- group 2: the p-column blocks TP, GP, AP, VP, PP
         T xTP[3], xGP[3], xAP[3], xVP[3], xPP[3];
         T sTP[3], sGP[3], sAP[3], sVP[3], sPP[3];
+#ifdef CPI_TRI_PSMEM
+#pragma unroll
+        for (int e = 0; e < 3; e++) { P.TP[e] = PST(18 + e); P.GP[e] = PST(21 + e); P.AP[e] = PST(24 + e); P.VP[e] = PST(27 + e); P.PP[e] = PST(30 + e); }
+#endif
 #pragma unroll
         for (int e = 0; e < 3; e++) { xTP[e] = P.TP[e]; xGP[e] = P.GP[e]; xAP[e] = P.AP[e]; xVP[e] = P.VP[e]; xPP[e] = P.PP[e]; }
 #pragma unroll
@@ -285,6 +319,10 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, const T* w, const T* ah, const T* g
             P.TP[e] = fma(dt6, sTP[e], P.TP[e]); P.GP[e] = fma(dt6, sGP[e], P.GP[e]); P.AP[e] = fma(dt6, sAP[e], P.AP[e]);
             P.VP[e] = fma(dt6, sVP[e], P.VP[e]); P.PP[e] = fma(dt6, sPP[e], P.PP[e]);
         }
+#ifdef CPI_TRI_PSMEM
+#pragma unroll
+        for (int e = 0; e < 3; e++) { PST(18 + e) = P.TP[e]; PST(21 + e) = P.GP[e]; PST(24 + e) = P.AP[e]; PST(27 + e) = P.VP[e]; PST(30 + e) = P.PP[e]; }
+#endif
     }
     CPI_FENCE();
 }
@@ -332,7 +370,13 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
     if (wid * TRI_WPW >= p.wpb || (int64_t)blockIdx.x * p.wpb + wid * TRI_WPW >= p.n_windows) return;   // whole warp idle (warp-uniform)
 
     T* sl = reinterpret_cast<T*>(smem_raw) + threadIdx.x;
+#ifdef CPI_TRI_PSMEM
+    T* ps = reinterpret_cast<T*>(smem_raw + SM_::off_fs) + threadIdx.x;
+    double fsr[TriL<MODEL>::NFS];
+#else
     double* fs = reinterpret_cast<double*>(smem_raw + SM_::off_fs) + threadIdx.x;
+    T* ps = nullptr;
+#endif
     // per-window scalar sets of the current 3 samples (the two idle lanes of a warp get a dummy slot of their own)
     double* sc = reinterpret_cast<double*>(smem_raw + SM_::off_sc) + (size_t)(lane_ok ? wslot : SM_::WPB + wid) * TriSC<MODEL>::STRIDE;
     const T* buf = reinterpret_cast<const T*>(smem_raw + SM_::off_buf + (size_t)wslot * TRI_BUF_STRIDE);
@@ -407,6 +451,10 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
     TriP<T> P;
 #pragma unroll
     for (int e = 0; e < 3; e++) P.TG[e] = P.TT[e] = P.GV[e] = P.TV[e] = P.AV[e] = P.VV[e] = P.TP[e] = P.GP[e] = P.AP[e] = P.VP[e] = P.PP[e] = T(0);
+#ifdef CPI_TRI_PSMEM
+#pragma unroll
+    for (int e = 0; e < 33; e++) PST(e) = T(0);
+#endif
 
 #pragma unroll 1
     for (int it0 = 0; it0 < wmax; it0 += 3) {
@@ -646,7 +694,7 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
                 for (int e = 0; e < 3; e++) { w_[e] = (T)wh[e]; a_[e] = (T)ah[e]; g_[e] = (T)g_tau[e]; }
 #pragma unroll
                 for (int e = 0; e < 9; e++) { R_[e] = (T)R[e]; Rm_[e] = (T)Rm[e]; R1_[e] = (T)R1[e]; }
-                tri_cov_step<MODEL, NT, T>(P, sl, w_, a_, g_, R_, Rm_, R1_, (T)pgg, (T)paa, (T)dt, (T)dt6, (T)p.q_w, (T)p.q_wb, (T)p.q_a, (T)p.q_ab, nx, pv);
+                tri_cov_step<MODEL, NT, T>(P, sl, ps, w_, a_, g_, R_, Rm_, R1_, (T)pgg, (T)paa, (T)dt, (T)dt6, (T)p.q_w, (T)p.q_wb, (T)p.q_a, (T)p.q_ab, nx, pv);
                 pgg += dt6 * (p.q_wb + 2.0 * p.q_wb + 2.0 * p.q_wb + p.q_wb);
                 paa += dt6 * (p.q_ab + 2.0 * p.q_ab + 2.0 * p.q_ab + p.q_ab);
             }
@@ -670,6 +718,13 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
     // ---- write the record (column-major 3x3 / 15x15, include/cpi_b200.h).  Lane c writes original column c (rows c, c+1, c+2).
     // symmetric diagonal blocks: average the two independently rounded copies of each off-diagonal entry (the reference
     // symmetrises every step, CpiV1.h:353)
+#ifdef CPI_TRI_PSMEM
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+        P.TG[e] = PST(e); P.TT[e] = PST(3 + e); P.GV[e] = PST(6 + e); P.TV[e] = PST(9 + e); P.AV[e] = PST(12 + e); P.VV[e] = PST(15 + e);
+        P.TP[e] = PST(18 + e); P.GP[e] = PST(21 + e); P.AP[e] = PST(24 + e); P.VP[e] = PST(27 + e); P.PP[e] = PST(30 + e);
+    }
+#endif
     T sTT[3], sVV[3], sPP[3];
     sTT[0] = P.TT[0]; sTT[1] = T(0.5) * (P.TT[1] + shf(P.TT[2], nx)); sTT[2] = T(0.5) * (P.TT[2] + shf(P.TT[1], pv));
     sVV[0] = P.VV[0]; sVV[1] = T(0.5) * (P.VV[1] + shf(P.VV[2], nx)); sVV[2] = T(0.5) * (P.VV[2] + shf(P.VV[1], pv));
@@ -714,6 +769,7 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
 
 #undef SLT
 #undef FST
+#undef PST
 #undef CN
 #undef KSUM
 
@@ -730,10 +786,9 @@ static cudaError_t launch_tri_one(const PreintParams& p0, int num_sms, cudaStrea
         if (e != cudaSuccess) return e;
         if (dev < 64) configured[dev] = true;
     }
-    // windows per block: one wave over all SMs if the batch fits (latency-bound regime), else the CTA capacity
-    const int64_t need = (p.n_windows + num_sms - 1) / num_sms;
-    constexpr int WPB = TriSmem<MODEL, T>::WPB;
-    if (p.wpb <= 0 || p.wpb > WPB) p.wpb = (int)(need <= WPB ? (need < 1 ? 1 : need) : WPB);
+    (void)num_sms;
+    constexpr int WPB = TriSmem<MODEL, T>::WPB;      // ten windows per one-warp CTA; the block scheduler spreads the CTAs over the SMs
+    p.wpb = WPB;
     const int grid = (int)((p.n_windows + p.wpb - 1) / p.wpb);
     kern<<<grid, TriSmem<MODEL, T>::NT, smem, st>>>(p);
     return cudaGetLastError();

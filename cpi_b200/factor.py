@@ -59,15 +59,25 @@ def factor_eval(model, states, records, lin, idx_i=None, idx_j=None, want_H1=Tru
     lib = capi.load()
     n = records.numel() // REC_DOUBLES[model]
     dev = records.device
+    for name, t in (("states", states), ("lin", lin), ("idx_i", idx_i), ("idx_j", idx_j)):
+        if t is not None and (not t.is_cuda or t.device != dev):
+            raise ValueError(f"{name} must be a CUDA tensor on {dev}")
+    if (idx_i is None) != (idx_j is None):
+        raise ValueError("idx_i and idx_j must both be given or both be None")
+    if idx_i is not None:
+        if idx_i.dtype != torch.int64 or idx_j.dtype != torch.int64 or idx_i.numel() != n or idx_j.numel() != n:
+            raise ValueError("idx_i / idx_j must be int64 tensors with one entry per factor")
+        idx_i = idx_i.contiguous(); idx_j = idx_j.contiguous()
     if out is None:
         e = torch.empty((n, 15), dtype=torch.float64, device=dev)
         H1 = torch.empty((n, 225), dtype=torch.float64, device=dev) if want_H1 else None
         H2 = torch.empty((n, 225), dtype=torch.float64, device=dev) if want_H2 else None
     else:
         e, H1, H2 = out
-    st = stream if stream is not None else torch.cuda.current_stream()
-    capi.check(lib.cpi_imu_factor_eval_batch(model, n, _tptr(states.contiguous()), _tptr(idx_i), _tptr(idx_j), _tptr(records.contiguous()),
-                                             _tptr(lin.contiguous()), _tptr(e), _tptr(H1), _tptr(H2), ctypes.c_void_p(st.cuda_stream)))
+    with torch.cuda.device(dev):
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        capi.check(lib.cpi_imu_factor_eval_batch(model, n, _tptr(states.contiguous()), _tptr(idx_i), _tptr(idx_j), _tptr(records.contiguous()),
+                                                 _tptr(lin.contiguous()), _tptr(e), _tptr(H1), _tptr(H2), ctypes.c_void_p(st.cuda_stream)))
     return e, H1, H2
 
 

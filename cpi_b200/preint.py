@@ -85,6 +85,10 @@ def preintegrate(model, samples, lin, sigmas, flags=0, offsets=None, ns=None, ou
     if samples.dtype not in (torch.float64, torch.float32) or lin.dtype != samples.dtype:
         raise ValueError("samples and lin must both be float64 or both float32")
     tdt = samples.dtype
+    dev = samples.device
+    for name, t in (("lin", lin), ("offsets", offsets), ("out", out)):
+        if t is not None and t.device != dev:
+            raise ValueError(f"{name} lives on {t.device}, samples on {dev}: all tensors of one call must be on the same CUDA device")
     samples = samples.contiguous(); lin = lin.contiguous()
     n = lin.numel() // 13
     avg = 1 if flags & FLAG_IMU_AVG else 0
@@ -103,9 +107,11 @@ def preintegrate(model, samples, lin, sigmas, flags=0, offsets=None, ns=None, ou
     elif out.numel() < n * REC_DOUBLES[model] or not out.is_contiguous() or out.dtype != tdt:
         raise ValueError("out must be a contiguous tensor of n_windows * record_doubles in the input dtype")
     sig = np.ascontiguousarray(sigmas, dtype=np.float64)
-    st = stream if stream is not None else torch.cuda.current_stream()
-    capi.check(lib.cpi_preintegrate_batch(model, 64 if tdt == torch.float64 else 32, n, _tptr(offsets), int(ns), _tptr(samples), _tptr(lin), _ptr(sig), int(flags),
-                                          _tptr(out), ctypes.c_void_p(st.cuda_stream)))
+    # the library launches on the CURRENT device: make the tensors' device current for the call and take its stream
+    with torch.cuda.device(dev):
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        capi.check(lib.cpi_preintegrate_batch(model, 64 if tdt == torch.float64 else 32, n, _tptr(offsets), int(ns), _tptr(samples), _tptr(lin), _ptr(sig), int(flags),
+                                              _tptr(out), ctypes.c_void_p(st.cuda_stream)))
     return out
 
 

@@ -31,6 +31,7 @@
 #ifndef CPI_B200_H
 #define CPI_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -91,7 +92,10 @@ extern "C" {
  *   sample_offsets device int64[n_windows+1], entry index (not bytes) of each window's first entry in `samples`;
  *                  or NULL for uniform windows of `ns_uniform` steps laid out back to back.
  *                  Window w has  steps = offsets[w+1]-offsets[w]  (minus 1 if CPI_FLAG_IMU_AVG).
- *   samples        device, CPI_SAMPLE_DOUBLES per entry
+ *   samples        device, CPI_SAMPLE_DOUBLES per entry.  The kernels stage every window's stream with 128-byte TMA bulk reads that
+ *                  start at the 16-byte boundary at or below the window's first entry: `samples` must be 16-byte aligned (any
+ *                  cudaMalloc / torch allocation is), so that no read begins before the buffer; reads never extend past the
+ *                  last entry of the buffer (the tail of every window is read with plain loads).
  *   lin            device, CPI_LIN_DOUBLES per window
  *   sigmas         HOST double[4] = {sigma_w, sigma_wb, sigma_a, sigma_ab}  (CpiBase ctor, CpiBase.h:52-57)
  *   out_records    device, CPI_REC_V1_DOUBLES (model 1) or CPI_REC_V2_DOUBLES (model 2) per window
@@ -103,11 +107,20 @@ int cpi_preintegrate_batch(int model, int dtype, int64_t n_windows,
                            const void* samples, const void* lin, const double* sigmas, int flags,
                            void* out_records, void* stream);
 
-/* Same with HOST buffers: pinned staging + H2D + kernel + D2H, synchronous.  sample_offsets is a HOST array. */
+/* Same with HOST buffers: H2D + kernel + D2H, synchronous, through device buffers owned by the library; batches above 16 MB are
+ * pipelined in up to 16 chunks (copy-in of chunk k+1 under the kernel of chunk k, copy-out under the next kernel).  sample_offsets
+ * is a HOST array.  The copies are cudaMemcpyAsync straight from / to the caller's buffers: PINNED buffers (cudaHostAlloc, or
+ * cpi_host_register below) overlap with the kernels; pageable buffers are legal but the CUDA driver stages them synchronously, so
+ * the pipeline degrades to copy-then-compute.  Calls from several host threads serialise on the library's scratch buffers. */
 int cpi_preintegrate_batch_host(int model, int dtype, int64_t n_windows,
                                 const int64_t* sample_offsets, int64_t ns_uniform,
                                 const void* samples, const void* lin, const double* sigmas, int flags,
                                 void* out_records);
+
+/* Pin / unpin a caller-owned host buffer for the *_host entry points (cudaHostRegister / cudaHostUnregister), for C callers that do
+ * not link the CUDA runtime themselves.  Registering is expensive (~ms per 100 MB): do it once per buffer, not per call. */
+int cpi_host_register(void* ptr, size_t bytes);
+int cpi_host_unregister(void* ptr);
 
 /* ---- factor evaluation ------------------------------------------------------------------------------------------- */
 
