@@ -52,6 +52,9 @@ WORKLOADS = {
     # configs[4]: the factor-evaluation kernel K3 over a 5k-keyframe chain (factors/s, HBM-write bound)
     "factor_5k": dict(model=1, n=4_999, ns=20, rate=200.0, factor=True,
                       desc="configs[4]: 5k-keyframe chain, batched ImuFactorCPIv1 residual + H1 + H2 (4 999 factors per step)"),
+    # bandwidth regime of K3 (not a BASELINE config): 1M factors = 4.5 GB of output per launch against the HBM write roofline
+    "factor_1m": dict(model=1, n=1_000_000, ns=20, rate=200.0, factor=True, distinct=20_000,
+                      desc="1M-factor chain, batched ImuFactorCPIv1 residual + H1 + H2 (bandwidth regime of the configs[4] kernel)"),
 }
 FFMA_PEAK_TFLOPS = 72.51   # same microbenchmark, fp32 FFMA
 DFMA_PEAK_TFLOPS = 34.17   # measured on this pool's B200 by tools/microbench.cu (profiles/microbench_r01.jsonl), burst == sustained
@@ -191,7 +194,11 @@ def run_factor(args, wl, emit=True, cpu=True):
     from cpi_b200 import synth
     from oracle.oracle import Oracle, Reference
     model, n, ns = wl["model"], wl["n"], wl["ns"]
-    S, L = synth.make_windows(n, ns, rate=wl["rate"], first_window=9000)
+    nd = min(n, wl.get("distinct", n))
+    S, L = synth.make_windows(nd, ns, rate=wl["rate"], first_window=9000)
+    if nd < n:      # tile a distinct block (host generation is ~0.1 ms per 20-sample window)
+        reps = (n + nd - 1) // nd
+        S = np.tile(S, (reps, 1, 1))[:n]; L = np.tile(L, (reps, 1))[:n]
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
@@ -217,6 +224,7 @@ def run_factor(args, wl, emit=True, cpu=True):
     outs = (torch.empty((n, 15), dtype=torch.float64, device="cuda"), torch.empty((n, 225), dtype=torch.float64, device="cuda"),
             torch.empty((n, 225), dtype=torch.float64, device="cuda"))
     flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2: written between timed launches
+    big = n > 100_000
     stream = torch.cuda.current_stream()
     t_settle = time.perf_counter()
     while time.perf_counter() - t_settle < 0.15:
@@ -240,22 +248,23 @@ def run_factor(args, wl, emit=True, cpu=True):
     P = lambda t: ctypes.c_void_p(t.data_ptr())
     def host_step():
         capi.check(lib.cpi_imu_factor_eval_batch_host(model, n, n + 1, P(hX), None, None, P(hR), P(hL), P(hE), P(hH1), P(hH2)))
-    for _ in range(3):
+    for _ in range(1 if big else 3):
         host_step()
+    ke = 2 if big else 10
     t0 = time.perf_counter()
-    for _ in range(10):
+    for _ in range(ke):
         host_step()
-    e2e_ms = (time.perf_counter() - t0) * 100.0
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / ke
     out = {"metric": "imu_factors_per_sec", "value": n / (ms * 1e-3), "unit": "factors/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": config_dict(wl, 1), "gpu_launches": int(launches), "kernel_ms": ms,
            "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
-                        "note": "4 496 algorithmic B/factor; at 5k factors (22 MB) the launch is latency-sized: 22 MB at peak would take 3.4 us"},
+                        "note": "4 496 algorithmic B/factor; at 5k factors (22 MB) the launch is latency-sized: 22 MB at peak would take 3.4 us; the 1M-factor workload shows the bandwidth regime"},
            "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "factors/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int((hX.numel() + hR.numel() + hL.numel()) * 8),
                    "d2h_bytes_per_step": int((hE.numel() + hH1.numel() + hH2.numel()) * 8), "api": "cpi_imu_factor_eval_batch_host"}}
     # one Levenberg-Marquardt step of the IMU-only chain entirely on device: eval -> information blocks -> block-tridiagonal
     # assembly -> block-cyclic-reduction Cholesky solve -> retract (parity unpinned: GTSAM is not in the tree)
-    if hasattr(factor, "chain_lm_step"):
+    if hasattr(factor, "chain_lm_step") and not big:
         try:
             factor.chain_lm_step(model, dX, dR, dL); torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -324,16 +324,18 @@ cudaError_t factor_launch(int model, const FactorParams& p, cudaStream_t st) {
     if (p.n == 0) return cudaSuccess;
     const size_t smem = (size_t)FPB * FTILE * sizeof(double);
     const int grid = (int)((p.n + FPB - 1) / FPB);
-    cudaError_t e;
-    if (model == 1) {
-        e = cudaFuncSetAttribute(k_factor_eval<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // the opt-in attribute is sticky per device context: set it once per device, not per launch
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_factor_eval<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_factor_eval<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k_factor_eval<1><<<grid, 128, smem, st>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(k_factor_eval<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_factor_eval<2><<<grid, 128, smem, st>>>(p);
+        if (dev < 64) configured[dev] = true;
     }
+    if (model == 1) k_factor_eval<1><<<grid, 128, smem, st>>>(p);
+    else k_factor_eval<2><<<grid, 128, smem, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -65,7 +65,7 @@ template <int MODEL, class T> struct TriSmem {
     static constexpr int WPB = TRI_WPW * NT / 32;                     // window slots per CTA
     static constexpr size_t off_fs = (size_t)TriL<MODEL>::NSL * NT * sizeof(T);
 #ifdef CPI_TRI_PSMEM
-    static constexpr size_t off_sc = off_fs + (size_t)33 * NT * sizeof(T);
+    static constexpr size_t off_sc = off_fs + (size_t)33 * NT * 8;
 #else
     static constexpr size_t off_sc = off_fs + (size_t)TriL<MODEL>::NFS * NT * 8;
 #endif
@@ -83,7 +83,7 @@ static_assert(TriSmem<2, double>::bytes <= 32182 - 1024, "model 2 fp64: 7 CTAs p
 #define SLT(e) sl[(e) * NT]
 #ifdef CPI_TRI_PSMEM        // experiment: covariance state parked in lane-private smem between groups, front state in registers
 #define FST(e) fsr[e]
-#define PST(e) ps[(e) * NT]
+#define PST(e) ps[(e) * NT]   /* ps is double* in this variant */
 #else
 #define FST(e) fs[(e) * NT]
 #endif
@@ -101,15 +101,17 @@ template <class T> CPI_DEV void negRt(const T* R, const T* u, T* o) {
     for (int i = 0; i < 3; i++) o[i] = -(R[i] * u[0] + R[3 + i] * u[1] + R[6 + i] * u[2]);
 }
 
-// Covariance state of one lane (column 0 of each block in the lane's frame)
+// Covariance state of one lane (column 0 of each block in the lane's frame).  Held in fp64 also by the fp32-storage variant: the
+// four RK4 stages run in T, but the state is ACCUMULATED in double (P += dt/6 * ksum), so 200 steps do not random-walk the
+// state's 24-bit rounding (worst 3x3 block of P vs the fp64 oracle: 1.9e-6 with a float state, ~1e-7 with a double one).
 template <class T> struct TriP {
-    T TG[3], TT[3], GV[3], TV[3], AV[3], VV[3], TP[3], GP[3], AP[3], VP[3], PP[3];
+    double TG[3], TT[3], GV[3], TV[3], AV[3], VV[3], TP[3], GP[3], AP[3], VP[3], PP[3];
 };
 
 // One RK4 step of the covariance (model 1: CpiV1.h:272-353).  w, ah: estimated readings; R, Rm, R1: old / mid / new
 // rotation (row-major, lane frame); pgg, paa: the scalar diagonal blocks P_bg,bg and P_ba,ba at the start of the step.
 template <int MODEL, int NT, class T>
-CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, T* ps, const T* w, const T* ah, const T* gt, const T* R, const T* Rm, const T* R1, T pgg, T paa, T dt, T dt6,
+CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah, const T* gt, const T* R, const T* Rm, const T* R1, T pgg, T paa, T dt, T dt6,
                           T q_w, T q_wb, T q_a, T q_ab, int nx, int pv) {
     const T hdt = dt * T(0.5);
     constexpr int NS = (MODEL == 1) ? 12 : 15;            // slot entries per stage
@@ -127,8 +129,11 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, T* ps, const T* w, const T* ah, con
         T xTG[3], xTT[3], xGV[3], xTV[3], xTC[3], xCV[3];
         T sTG[3], sTT[3], sGV[3], sTV[3];
         T G1s[3], G2s[3], tts[3];                             // model 2: TG(start) columns 1, 2 and TT(start) entries 11, 21, 22
+        T oTG[3], oTT[3], oGV[3], oTV[3];                     // start-of-step values in the arithmetic type
 #pragma unroll
-        for (int e = 0; e < 3; e++) { xTG[e] = P.TG[e]; xTT[e] = P.TT[e]; xGV[e] = P.GV[e]; xTV[e] = P.TV[e]; xTC[e] = P.TT[e]; xCV[e] = P.TV[e]; }
+        for (int e = 0; e < 3; e++) { oTG[e] = (T)P.TG[e]; oTT[e] = (T)P.TT[e]; oGV[e] = (T)P.GV[e]; oTV[e] = (T)P.TV[e]; }
+#pragma unroll
+        for (int e = 0; e < 3; e++) { xTG[e] = oTG[e]; xTT[e] = oTT[e]; xGV[e] = oGV[e]; xTV[e] = oTV[e]; xTC[e] = oTT[e]; xCV[e] = oTV[e]; }
 #pragma unroll
         for (int s = 0; s < 4; s++) {
             const T* Rs = (s == 0) ? R : (s == 3 ? R1 : Rm);
@@ -178,33 +183,33 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, T* ps, const T* w, const T* ah, con
             T kTC[3], kCV[3];
             if (MODEL == 2) {
                 // GV += TG(start)^T C_s[0,:]^T ;  TV += TC C_s[0,:]^T
-                kGV[0] += P.TG[0] * c0[0] + P.TG[1] * c0[1] + P.TG[2] * c0[2];
+                kGV[0] += oTG[0] * c0[0] + oTG[1] * c0[1] + oTG[2] * c0[2];
                 kGV[1] += G1s[0] * c0[0] + G1s[1] * c0[1] + G1s[2] * c0[2];
                 kGV[2] += G2s[0] * c0[0] + G2s[1] * c0[1] + G2s[2] * c0[2];
 #pragma unroll
                 for (int e = 0; e < 3; e++) kTV[e] += xTC[e] * c0[0] + TC1[e] * c0[1] + TC2[e] * c0[2];
                 // TC:  -W TC - TG(start)^T  (column 0: minus row 0 of TG(start))
                 cross(xTC, w, kTC);
-                kTC[0] -= P.TG[0]; kTC[1] -= G1s[0]; kTC[2] -= G2s[0];
+                kTC[0] -= oTG[0]; kTC[1] -= G1s[0]; kTC[2] -= G2s[0];
                 // CV:  TC^T A_s[0,:]^T + TT(start) C_s[0,:]^T
-                kCV[0] = (xTC[0] * a0[0] + xTC[1] * a0[1] + xTC[2] * a0[2]) + (P.TT[0] * c0[0] + P.TT[1] * c0[1] + P.TT[2] * c0[2]);
-                kCV[1] = (TC1[0] * a0[0] + TC1[1] * a0[1] + TC1[2] * a0[2]) + (P.TT[1] * c0[0] + tts[0] * c0[1] + tts[1] * c0[2]);
-                kCV[2] = (TC2[0] * a0[0] + TC2[1] * a0[1] + TC2[2] * a0[2]) + (P.TT[2] * c0[0] + tts[1] * c0[1] + tts[2] * c0[2]);
+                kCV[0] = (xTC[0] * a0[0] + xTC[1] * a0[1] + xTC[2] * a0[2]) + (oTT[0] * c0[0] + oTT[1] * c0[1] + oTT[2] * c0[2]);
+                kCV[1] = (TC1[0] * a0[0] + TC1[1] * a0[1] + TC1[2] * a0[2]) + (oTT[1] * c0[0] + tts[0] * c0[1] + tts[1] * c0[2]);
+                kCV[2] = (TC2[0] * a0[0] + TC2[1] * a0[1] + TC2[2] * a0[2]) + (oTT[2] * c0[0] + tts[1] * c0[1] + tts[2] * c0[2]);
             }
 #pragma unroll
             for (int e = 0; e < 3; e++) {
                 sTG[e] = KSUM(sTG[e], kTG[e], s); sTT[e] = KSUM(sTT[e], kTT[e], s); sGV[e] = KSUM(sGV[e], kGV[e], s); sTV[e] = KSUM(sTV[e], kTV[e], s);
                 if (s < 3) {
-                    xTG[e] = fma(kTG[e], CN(s), P.TG[e]); xTT[e] = fma(kTT[e], CN(s), P.TT[e]); xGV[e] = fma(kGV[e], CN(s), P.GV[e]);
-                    xTV[e] = fma(kTV[e], CN(s), P.TV[e]);
-                    if (MODEL == 2) { xTC[e] = fma(kTC[e], CN(s), P.TT[e]); xCV[e] = fma(kCV[e], CN(s), P.TV[e]); }
+                    xTG[e] = fma(kTG[e], CN(s), oTG[e]); xTT[e] = fma(kTT[e], CN(s), oTT[e]); xGV[e] = fma(kGV[e], CN(s), oGV[e]);
+                    xTV[e] = fma(kTV[e], CN(s), oTV[e]);
+                    if (MODEL == 2) { xTC[e] = fma(kTC[e], CN(s), oTT[e]); xCV[e] = fma(kCV[e], CN(s), oTV[e]); }
                 }
             }
         }
 #pragma unroll
         for (int e = 0; e < 3; e++) {
-            P.TG[e] = fma(dt6, sTG[e], P.TG[e]); P.TT[e] = fma(dt6, sTT[e], P.TT[e]); P.GV[e] = fma(dt6, sGV[e], P.GV[e]);
-            P.TV[e] = fma(dt6, sTV[e], P.TV[e]);
+            P.TG[e] = fma((double)dt6, (double)sTG[e], P.TG[e]); P.TT[e] = fma((double)dt6, (double)sTT[e], P.TT[e]);
+            P.GV[e] = fma((double)dt6, (double)sGV[e], P.GV[e]); P.TV[e] = fma((double)dt6, (double)sTV[e], P.TV[e]);
         }
 #ifdef CPI_TRI_PSMEM
 #pragma unroll
@@ -213,13 +218,13 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, T* ps, const T* w, const T* ah, con
     }
     CPI_FENCE();
     {   // ---- group 1b: AV, VV (need TV's stage values)
-        T xAV[3], xVV[3], sAV[3], sVV[3];
+        T xAV[3], xVV[3], sAV[3], sVV[3], oAV[3], oVV[3];
 #ifdef CPI_TRI_PSMEM
 #pragma unroll
         for (int e = 0; e < 3; e++) { P.AV[e] = PST(12 + e); P.VV[e] = PST(15 + e); }
 #endif
 #pragma unroll
-        for (int e = 0; e < 3; e++) { xAV[e] = P.AV[e]; xVV[e] = P.VV[e]; }
+        for (int e = 0; e < 3; e++) { oAV[e] = (T)P.AV[e]; oVV[e] = (T)P.VV[e]; xAV[e] = oAV[e]; xVV[e] = oVV[e]; }
 #pragma unroll
         for (int s = 0; s < 4; s++) {
             const T* Rs = (s == 0) ? R : (s == 3 ? R1 : Rm);
@@ -253,11 +258,11 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, T* ps, const T* w, const T* ah, con
 #pragma unroll
             for (int e = 0; e < 3; e++) {
                 sAV[e] = KSUM(sAV[e], kAV[e], s); sVV[e] = KSUM(sVV[e], kVV[e], s);
-                if (s < 3) { xAV[e] = fma(kAV[e], CN(s), P.AV[e]); xVV[e] = fma(kVV[e], CN(s), P.VV[e]); }
+                if (s < 3) { xAV[e] = fma(kAV[e], CN(s), oAV[e]); xVV[e] = fma(kVV[e], CN(s), oVV[e]); }
             }
         }
 #pragma unroll
-        for (int e = 0; e < 3; e++) { P.AV[e] = fma(dt6, sAV[e], P.AV[e]); P.VV[e] = fma(dt6, sVV[e], P.VV[e]); }
+        for (int e = 0; e < 3; e++) { P.AV[e] = fma((double)dt6, (double)sAV[e], P.AV[e]); P.VV[e] = fma((double)dt6, (double)sVV[e], P.VV[e]); }
 #ifdef CPI_TRI_PSMEM
 #pragma unroll
         for (int e = 0; e < 3; e++) { PST(12 + e) = P.AV[e]; PST(15 + e) = P.VV[e]; }
@@ -265,14 +270,16 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, T* ps, const T* w, const T* ah, con
     }
     CPI_FENCE();
     {   // ---- group 2: the p-column blocks TP, GP, AP, VP, PP
-        T xTP[3], xGP[3], xAP[3], xVP[3], xPP[3];
+        T xTP[3], xGP[3], xAP[3], xVP[3], oTP[3], oGP[3], oAP[3], oVP[3];
         T sTP[3], sGP[3], sAP[3], sVP[3], sPP[3];
 #ifdef CPI_TRI_PSMEM
 #pragma unroll
         for (int e = 0; e < 3; e++) { P.TP[e] = PST(18 + e); P.GP[e] = PST(21 + e); P.AP[e] = PST(24 + e); P.VP[e] = PST(27 + e); P.PP[e] = PST(30 + e); }
 #endif
 #pragma unroll
-        for (int e = 0; e < 3; e++) { xTP[e] = P.TP[e]; xGP[e] = P.GP[e]; xAP[e] = P.AP[e]; xVP[e] = P.VP[e]; xPP[e] = P.PP[e]; }
+        for (int e = 0; e < 3; e++) { oTP[e] = (T)P.TP[e]; oGP[e] = (T)P.GP[e]; oAP[e] = (T)P.AP[e]; oVP[e] = (T)P.VP[e]; }
+#pragma unroll
+        for (int e = 0; e < 3; e++) { xTP[e] = oTP[e]; xGP[e] = oGP[e]; xAP[e] = oAP[e]; xVP[e] = oVP[e]; }
 #pragma unroll
         for (int s = 0; s < 4; s++) {
             const T* Rs = (s == 0) ? R : (s == 3 ? R1 : Rm);
@@ -293,7 +300,7 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, T* ps, const T* w, const T* ah, con
                 if (MODEL == 2) {                             // + C_s CP_0,  CP_s = TP(start) + CN(s-1) CV_{s-1}
                     T cp[3], u2[3];
 #pragma unroll
-                    for (int e = 0; e < 3; e++) cp[e] = (s == 0) ? P.TP[e] : fma((T)SLT((s - 1) * NS + 12 + e), CN(s - 1), P.TP[e]);
+                    for (int e = 0; e < 3; e++) cp[e] = (s == 0) ? oTP[e] : fma((T)SLT((s - 1) * NS + 12 + e), CN(s - 1), oTP[e]);
                     cross(gt, cp, u2);
 #pragma unroll
                     for (int e = 0; e < 3; e++) u[e] += u2[e];
@@ -309,15 +316,16 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, T* ps, const T* w, const T* ah, con
                 sTP[e] = KSUM(sTP[e], kTP[e], s); sGP[e] = KSUM(sGP[e], gv[e], s); sAP[e] = KSUM(sAP[e], av[e], s);
                 sVP[e] = KSUM(sVP[e], kVP[e], s); sPP[e] = KSUM(sPP[e], kPP[e], s);
                 if (s < 3) {
-                    xTP[e] = fma(kTP[e], CN(s), P.TP[e]); xGP[e] = fma(gv[e], CN(s), P.GP[e]); xAP[e] = fma(av[e], CN(s), P.AP[e]);
-                    xVP[e] = fma(kVP[e], CN(s), P.VP[e]);
+                    xTP[e] = fma(kTP[e], CN(s), oTP[e]); xGP[e] = fma(gv[e], CN(s), oGP[e]); xAP[e] = fma(av[e], CN(s), oAP[e]);
+                    xVP[e] = fma(kVP[e], CN(s), oVP[e]);
                 }
             }
         }
 #pragma unroll
         for (int e = 0; e < 3; e++) {
-            P.TP[e] = fma(dt6, sTP[e], P.TP[e]); P.GP[e] = fma(dt6, sGP[e], P.GP[e]); P.AP[e] = fma(dt6, sAP[e], P.AP[e]);
-            P.VP[e] = fma(dt6, sVP[e], P.VP[e]); P.PP[e] = fma(dt6, sPP[e], P.PP[e]);
+            P.TP[e] = fma((double)dt6, (double)sTP[e], P.TP[e]); P.GP[e] = fma((double)dt6, (double)sGP[e], P.GP[e]);
+            P.AP[e] = fma((double)dt6, (double)sAP[e], P.AP[e]); P.VP[e] = fma((double)dt6, (double)sVP[e], P.VP[e]);
+            P.PP[e] = fma((double)dt6, (double)sPP[e], P.PP[e]);
         }
 #ifdef CPI_TRI_PSMEM
 #pragma unroll
@@ -371,11 +379,11 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
 
     T* sl = reinterpret_cast<T*>(smem_raw) + threadIdx.x;
 #ifdef CPI_TRI_PSMEM
-    T* ps = reinterpret_cast<T*>(smem_raw + SM_::off_fs) + threadIdx.x;
+    double* ps = reinterpret_cast<double*>(smem_raw + SM_::off_fs) + threadIdx.x;
     double fsr[TriL<MODEL>::NFS];
 #else
     double* fs = reinterpret_cast<double*>(smem_raw + SM_::off_fs) + threadIdx.x;
-    T* ps = nullptr;
+    double* ps = nullptr;
 #endif
     // per-window scalar sets of the current 3 samples (the two idle lanes of a warp get a dummy slot of their own)
     double* sc = reinterpret_cast<double*>(smem_raw + SM_::off_sc) + (size_t)(lane_ok ? wslot : SM_::WPB + wid) * TriSC<MODEL>::STRIDE;
@@ -450,10 +458,10 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
     double DT = 0.0, pgg = 0.0, paa = 0.0;
     TriP<T> P;
 #pragma unroll
-    for (int e = 0; e < 3; e++) P.TG[e] = P.TT[e] = P.GV[e] = P.TV[e] = P.AV[e] = P.VV[e] = P.TP[e] = P.GP[e] = P.AP[e] = P.VP[e] = P.PP[e] = T(0);
+    for (int e = 0; e < 3; e++) P.TG[e] = P.TT[e] = P.GV[e] = P.TV[e] = P.AV[e] = P.VV[e] = P.TP[e] = P.GP[e] = P.AP[e] = P.VP[e] = P.PP[e] = 0.0;
 #ifdef CPI_TRI_PSMEM
 #pragma unroll
-    for (int e = 0; e < 33; e++) PST(e) = T(0);
+    for (int e = 0; e < 33; e++) PST(e) = 0.0;
 #endif
 
 #pragma unroll 1
@@ -725,10 +733,10 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
         P.TP[e] = PST(18 + e); P.GP[e] = PST(21 + e); P.AP[e] = PST(24 + e); P.VP[e] = PST(27 + e); P.PP[e] = PST(30 + e);
     }
 #endif
-    T sTT[3], sVV[3], sPP[3];
-    sTT[0] = P.TT[0]; sTT[1] = T(0.5) * (P.TT[1] + shf(P.TT[2], nx)); sTT[2] = T(0.5) * (P.TT[2] + shf(P.TT[1], pv));
-    sVV[0] = P.VV[0]; sVV[1] = T(0.5) * (P.VV[1] + shf(P.VV[2], nx)); sVV[2] = T(0.5) * (P.VV[2] + shf(P.VV[1], pv));
-    sPP[0] = P.PP[0]; sPP[1] = T(0.5) * (P.PP[1] + shf(P.PP[2], nx)); sPP[2] = T(0.5) * (P.PP[2] + shf(P.PP[1], pv));
+    double sTT[3], sVV[3], sPP[3];
+    sTT[0] = P.TT[0]; sTT[1] = 0.5 * (P.TT[1] + shf(P.TT[2], nx)); sTT[2] = 0.5 * (P.TT[2] + shf(P.TT[1], pv));
+    sVV[0] = P.VV[0]; sVV[1] = 0.5 * (P.VV[1] + shf(P.VV[2], nx)); sVV[2] = 0.5 * (P.VV[2] + shf(P.VV[1], pv));
+    sPP[0] = P.PP[0]; sPP[1] = 0.5 * (P.PP[1] + shf(P.PP[2], nx)); sPP[2] = 0.5 * (P.PP[2] + shf(P.PP[1], pv));
     if (!active) return;
     constexpr int RD = (MODEL == 1) ? CPI_REC_V1_DOUBLES : CPI_REC_V2_DOUBLES;
     T* rec = reinterpret_cast<T*>(p.out) + win * (int64_t)RD;
@@ -759,9 +767,9 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const int r = ri[k];
-        put2(0, 0, r, sTT[k]); put2(2, 2, r, sVV[k]); put2(4, 4, r, sPP[k]);
-        put2(0, 1, r, P.TG[k]); put2(1, 2, r, P.GV[k]); put2(0, 2, r, P.TV[k]); put2(3, 2, r, P.AV[k]);
-        put2(0, 4, r, P.TP[k]); put2(1, 4, r, P.GP[k]); put2(3, 4, r, P.AP[k]); put2(2, 4, r, P.VP[k]);
+        put2(0, 0, r, (T)sTT[k]); put2(2, 2, r, (T)sVV[k]); put2(4, 4, r, (T)sPP[k]);
+        put2(0, 1, r, (T)P.TG[k]); put2(1, 2, r, (T)P.GV[k]); put2(0, 2, r, (T)P.TV[k]); put2(3, 2, r, (T)P.AV[k]);
+        put2(0, 4, r, (T)P.TP[k]); put2(1, 4, r, (T)P.GP[k]); put2(3, 4, r, (T)P.AP[k]); put2(2, 4, r, (T)P.VP[k]);
         put2(1, 1, r, r == c ? (T)pgg : T(0)); put2(3, 3, r, r == c ? (T)paa : T(0));
         put2(0, 3, r, T(0)); put2(1, 3, r, T(0));                    // P_theta,ba = P_bg,ba = 0 identically
     }
