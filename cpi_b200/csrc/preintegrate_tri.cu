@@ -353,6 +353,17 @@ CPI_DEV void rot_col(double a, double b, const double* w, const double* v, doubl
 
 // Scalars of one sample that depend on the raw sample and the bias only -- NOT on the recurrence (CpiV1.h:97-142, 162-164, 196-238):
 // rotation coefficients of the full and the half step, f1..f4, and (model 1) the d f/d|w| terms and the right-Jacobian coefficients.
+// Profiling-only builds (never shipped; tools/phase_builds.sh): the two phases the north_star wants measured separately.
+//   CPI_TRI_PHASE_LOAD  the TMA sample stream alone (stage, wait, read; no arithmetic)  -> achieved HBM GB/s of the sample-load phase
+//   CPI_TRI_PHASE_COV   the covariance RK4 alone on constant inputs (no fetch, no front)   -> fp64 FLOP/s of the covariance phase
+#if defined(CPI_TRI_PHASE_LOAD)
+constexpr bool kLoadOnly = true, kCovOnly = false;
+#elif defined(CPI_TRI_PHASE_COV)
+constexpr bool kLoadOnly = false, kCovOnly = true;
+#else
+constexpr bool kLoadOnly = false, kCovOnly = false;
+#endif
+
 enum : int { SC_A1 = 0, SC_B1, SC_A2, SC_B2, SC_F1, SC_F2, SC_F3, SC_F4, SC_DT6, SC_D1, SC_D2, SC_D3, SC_D4, SC_CA, SC_CB, SC_N };
 
 template <int MODEL, class T>
@@ -471,7 +482,7 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
         {
             const int is = it0 + c;
             double w0 = 0.0, w1 = 0.0, w2 = 0.0, dt = 0.0;
-            if (is < nsteps) {
+            if (is < nsteps && !kCovOnly) {
                 bool sm_;
                 const T* src = sample_ptr(is, sm_);
                 if (sm_) { w0 = (double)src[0]; w1 = (double)src[1]; w2 = (double)src[2]; dt = (double)src[6]; }
@@ -489,7 +500,8 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
             double v[SC_N];
 #pragma unroll
             for (int e = 0; e < SC_N; e++) v[e] = 0.0;
-            if (!null_step) {
+            if (kLoadOnly || kCovOnly) v[SC_A1] = w0 + w1 + w2 + dt;
+            else if (!null_step) {
                 const double hd = 0.5 * dt, dt2 = dt * dt, dt3 = dt2 * dt;
                 v[SC_DT6] = dt / 6.0;                                // CpiV1.h:352
                 if (small_w) {                                       // Taylor forms: CpiV1.h:119-120, 132-136, 162-164, 196-216, 267-268
@@ -533,7 +545,8 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
             if (it >= wmax) break;                                   // warp-uniform
             // ---- fetch entry `it` in the lane frame; finished windows run a NULL step
             double wm[3] = {0, 0, 0}, am[3] = {0, 0, 0}, dt = 0.0;
-            if (it < nsteps) {
+            if (kCovOnly) { wm[0] = 0.1; wm[1] = -0.2; wm[2] = 0.3; am[0] = 0.1; am[1] = 0.2; am[2] = 9.8; dt = 0.005; }
+            else if (it < nsteps) {
                 bool sm_;
                 const T* src = sample_ptr(it, sm_);
                 if (sm_) {
@@ -547,9 +560,10 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
                 }
             }
             DT += dt;                                                // CpiV1.h:69 (before the dt == 0 return)
+            if (kLoadOnly) { DT += wm[0] + wm[1] + wm[2] + am[0] + am[1] + am[2]; continue; }
             const double* scj = sc + j * TriSC<MODEL>::PER;
             const double a1 = scj[SC_A1], b1 = scj[SC_B1], a2 = scj[SC_A2], b2 = scj[SC_B2];
-            const double f1 = scj[SC_F1], f2 = scj[SC_F2], f3 = scj[SC_F3], f4 = scj[SC_F4], dt6 = scj[SC_DT6];
+            const double f1 = scj[SC_F1], f2 = scj[SC_F2], f3 = scj[SC_F3], f4 = scj[SC_F4], dt6 = kCovOnly ? dt / 6.0 : scj[SC_DT6];
 
             // ---- estimated readings (CpiV1.h:77-86)
             const double wh[3] = {wm[0] - FST(FS_BW), wm[1] - FST(FS_BW + 1), wm[2] - FST(FS_BW + 2)};
@@ -563,7 +577,10 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
 
             // ---- relative rotation: own column of the new and the mid-point rotation (CpiV1.h:119-124, 267-269), then the full matrices
             double R1[9], Rm[9];
-            {
+            if (kCovOnly) {
+#pragma unroll
+                for (int e = 0; e < 9; e++) { R1[e] = R[e]; Rm[e] = R[e]; }
+            } else {
                 const double rc[3] = {R[0], R[3], R[6]};
                 double r1c[3], rmc[3], X1[3], X2[3];
                 rot_col2(a1, b1, a2, b2, wh, rc, r1c, rmc);
@@ -575,6 +592,7 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
                 for (int e = 0; e < 3; e++) { Rm[3 * e] = rmc[e]; Rm[3 * e + 1] = X1[e]; Rm[3 * e + 2] = X2[e]; }
             }
 
+            if (!kCovOnly) {
             // ---- means (CpiV1.h:145-154):  alpha += beta dt + R1^T alpha_arg a ;  beta += R1^T beta_arg a   (old beta); this lane owns element c
             const double hdt2 = (dt * dt) * 0.5;
             double Wa[3], W2a[3], ua[3], ub[3];
@@ -692,6 +710,7 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
                     FST(FS_DPL + e) = dt6 * (2.0 * (l0[e] * hdt) + 2.0 * (lm[e] * hdt) + lm[e] * dt) + Ppv * dvl + FST(FS_DPL + e);
                     FST(FS_DVL + e) = dt6 * (l0[e] + 2.0 * lm[e] + 2.0 * lm[e] + l1[e]) + dvl;
                 }
+            }
             }
             CPI_FENCE();
 

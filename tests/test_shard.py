@@ -67,3 +67,44 @@ def test_sharded_gather_matches_unsharded(oracle, world, model, flags, ragged):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res          # every rank holds every record, bit-identical to the unsharded run
+
+
+def _worker_edge(rank, world, port, mode, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle import Oracle
+    orc = Oracle()
+    n, ns = (2, 6) if mode == "empty_rank" else (7, 6)        # n = 2 on 3 ranks: ceil(2/3) = 1 -> rank 2 holds no real window
+    S, L = synth.make_windows(n, ns)
+
+    def compute(model, s, l, sig, fl, loc, ns_loc, out):
+        if mode == "fail" and rank == 1:
+            raise ValueError("injected failure on rank 1")
+        out.copy_(torch.from_numpy(orc.preintegrate(model, s, l, sig, fl, offsets=loc, ns=ns_loc)))
+
+    try:
+        got = shard.preintegrate_sharded(1, S.reshape(-1, 7), L, synth.SIGMAS, 0, ns=ns, compute=compute).numpy()
+        ok = bool(np.array_equal(got, orc.preintegrate(1, S.reshape(-1, 7), L, synth.SIGMAS, 0, ns=ns)))
+        q.put((rank, "ok" if ok else "mismatch"))
+    except RuntimeError as e:
+        q.put((rank, "raised"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["empty_rank", "fail"])
+def test_sharded_edge_cases(oracle, mode):
+    """(a) a rank whose shard holds no real window still takes part in the collective (zero-step padding windows);
+    (b) a local failure on one rank is raised on EVERY rank instead of leaving the others blocked in the all-gather."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_edge, args=(r, world, port, mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert set(res.values()) == ({"ok"} if mode == "empty_rank" else {"raised"}), res
