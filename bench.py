@@ -306,10 +306,37 @@ class Ctx:
             torch.cuda.set_device(0)
         capi.load()
         self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.numa = None
+        if self.world > 1:
+            self.numa = self.pin_to_gpu_numa_node(torch)
         self.comm = None
         if self.world > 1:
             from cpi_b200 import shard
             self.comm = shard.Communicator()      # the product's NCCL communicator (C ABI)
+
+
+def _pin_to_gpu_numa_node(self, torch):
+    """N > 1: bind this rank (and therefore its pinned host buffers, first-touch) to the CPUs of its GPU's NUMA node, so that eight
+    ranks do not push their H2D traffic through one socket.  Best effort: silently skipped when sysfs does not say."""
+    try:
+        pr = torch.cuda.get_device_properties(self.dev)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(f"{base}/numa_node").read())
+        cpus = set()
+        for part in open(f"{base}/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"node": node, "cpus": len(cpus)}
+    except Exception:      # noqa: BLE001
+        pass
+    return None
+
+
+Ctx.pin_to_gpu_numa_node = _pin_to_gpu_numa_node
 
 
 def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=False, clocks=True):
@@ -458,6 +485,8 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
         out["e2e"] = {"value": world * n / (e2e_ms * 1e-3), "unit": "windows/s", "ms_per_step": e2e_ms,
                       "h2d_bytes_per_step": int(hS.numel() * es + hL.numel() * es), "d2h_bytes_per_step": int(hO.numel() * es),
                       "api": "cpi_preintegrate_batch_host (C ABI, pinned host buffers)"}
+        if ctx.numa:
+            out["e2e"]["host_numa"] = f"every rank bound to the NUMA node of its GPU (rank 0: node {ctx.numa['node']}, {ctx.numa['cpus']} cpus) before allocating its pinned buffers"
         del hS, hL, hO
     del batches, gathers
     torch.cuda.empty_cache()
