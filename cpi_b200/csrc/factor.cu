@@ -52,8 +52,15 @@ __global__ void __launch_bounds__(128) k_factor_eval(const FactorParams p) {
     const int nf = (int)((p.n - f0) < FPB ? (p.n - f0) : FPB);
     const bool wantH1 = p.H1 != nullptr, wantH2 = p.H2 != nullptr;
 
-    // zero the tile cooperatively (most of H1/H2 is structural zero)
-    for (int k = tid; k < FPB * FTILE; k += blockDim.x) tile[k] = 0.0;
+    // Three sub-tiles laid out exactly like the CTA's three contiguous output ranges (e: FPB x 15, H1 / H2: FPB x 225), so that the
+    // stream-out is a straight 16-byte-vector copy.  Zero them cooperatively (most of H1/H2 is structural zero).
+    double* tE = tile;
+    double* tH1 = tile + FPB * 15;
+    double* tH2 = tH1 + FPB * 225;
+    {
+        double2* t2 = reinterpret_cast<double2*>(tile);
+        for (int k = tid; k < FPB * FTILE / 2; k += blockDim.x) t2[k] = make_double2(0.0, 0.0);
+    }
     __syncthreads();
 
     if (tid < nf) {
@@ -64,9 +71,9 @@ __global__ void __launch_bounds__(128) k_factor_eval(const FactorParams p) {
         const double* xj = p.states + ib * CPI_STATE_DOUBLES;
         const double* r = p.records + f * (int64_t)RD;
         const double* l = p.lin + f * CPI_LIN_DOUBLES;
-        double* E = tile + (size_t)tid * FTILE;
-        double* H1 = E + 15;
-        double* H2 = E + 240;
+        double* E = tE + tid * 15;
+        double* H1 = tH1 + tid * 225;
+        double* H2 = tH2 + tid * 225;
 
         double qK[4], qK1[4], bgK[3], bgK1[3], vK[3], vK1[3], baK[3], baK1[3], pK[3], pK1[3];
 #pragma unroll
@@ -187,10 +194,21 @@ __global__ void __launch_bounds__(128) k_factor_eval(const FactorParams p) {
     }
     __syncthreads();
 
-    // coalesced stream-out: three contiguous ranges per CTA
-    for (int k = tid; k < nf * 15; k += blockDim.x) p.e[f0 * 15 + k] = tile[(k / 15) * FTILE + (k % 15)];
-    if (wantH1) for (int k = tid; k < nf * 225; k += blockDim.x) p.H1[f0 * 225 + k] = tile[(k / 225) * FTILE + 15 + (k % 225)];
-    if (wantH2) for (int k = tid; k < nf * 225; k += blockDim.x) p.H2[f0 * 225 + k] = tile[(k / 225) * FTILE + 240 + (k % 225)];
+    // coalesced stream-out: three contiguous ranges per CTA, 16 bytes per lane (f0 is a multiple of FPB = 16, so every range starts
+    // 16-byte aligned when the caller's arrays are; the last element of an odd-length range goes out as a single double)
+    auto copy_out = [&](double* dst, const double* src, int n) {
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            double2* d2 = reinterpret_cast<double2*>(dst);
+            const double2* s2 = reinterpret_cast<const double2*>(src);
+            for (int k = tid; k < n / 2; k += blockDim.x) d2[k] = s2[k];
+            if ((n & 1) && tid == 0) dst[n - 1] = src[n - 1];
+        } else {
+            for (int k = tid; k < n; k += blockDim.x) dst[k] = src[k];
+        }
+    };
+    copy_out(p.e + f0 * 15, tE, nf * 15);
+    if (wantH1) copy_out(p.H1 + f0 * 225, tH1, nf * 225);
+    if (wantH2) copy_out(p.H2 + f0 * 225, tH2, nf * 225);
 }
 
 // ---- getpredictedstate_v1/_v2 (GraphSolver_IMU.cpp:263-307): one thread per window -------------------------------------
