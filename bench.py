@@ -301,7 +301,8 @@ class Ctx:
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             torch.cuda.set_device(local)
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            import datetime
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
         else:
             torch.cuda.set_device(0)
         capi.load()
@@ -400,6 +401,9 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
         ctx.comm.wait(stream)
     launches0 = capi.launch_count()
     gc.collect(); gc.disable()        # no collector pauses inside the timed region
+    # Two NCCL communicators (the product's and torch's) must never have collectives in flight at the same time on the same devices
+    # (their kernels could start in different orders on different ranks and wait for each other): drain the device BEFORE the barrier.
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

@@ -228,6 +228,8 @@ int64_t cpi_cut_windows(int64_t n_imu, const double* t, const double* w, const d
  *        overlaps the collective.  Re-using a gather buffer orders the new kernel behind that buffer's previous all-gather.
  *        n_local must be the same on every rank (pad a short last shard with zero-step windows).
  *   cpi_comm_wait        makes `stream` wait for the most recently enqueued all-gather (call before consuming the records)
+ * The usual NCCL rule applies: collectives of ANOTHER communicator on the same devices (e.g. an MPI / torch.distributed NCCL group)
+ * must not be in flight at the same time as this communicator's all-gathers -- synchronise the device between the two.
  */
 #define CPI_COMM_ID_BYTES 128
 typedef struct cpi_comm cpi_comm;

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Parity report at scale: the CUDA path (through the C ABI) against the UNMODIFIED reference compiled in place
 (oracle/_ref/libcpi_ref.so, all host threads) on the bench distribution.  Writes one JSON object to stdout.
-Run on the GPU box:  python tools/parity_report.py > gpurun_out/parity_r01.json"""
+Run on the GPU box:  python tools/parity_report.py > gpurun_out/parity_r02.json"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
@@ -11,7 +11,7 @@ from oracle.oracle import Reference
 from parity import REC, window_band
 
 R = Reference()
-cores = os.cpu_count() or 1
+cores = synth.usable_cpus()
 FIELDS = ["R", "alpha", "beta", "J_q", "J_a", "J_b", "H_a", "H_b", "P"]
 
 
@@ -58,8 +58,27 @@ S, L = synth.make_windows(4000, 200)
 S32, L32 = S.astype(np.float32), L.astype(np.float32)
 ref = R.preintegrate(1, S32.astype(np.float64), L32.astype(np.float64), synth.SIGMAS, 0, ns=200, nthreads=cores)
 got = preint.preintegrate_host(1, S32, L32, synth.SIGMAS, 0, ns=200).astype(np.float64)
-report["cases"].append({"model": 1, "dtype": "fp32 storage", "windows": 4000, "samples": 200,
+report["cases"].append({"model": 1, "dtype": "fp32 storage (fp32 RK4 stages, fp64-accumulated state)", "windows": 4000, "samples": 200,
                         "worst_error_over_all_windows": field_errors(got, ref, 1, window_band(S.reshape(-1, 7), np.arange(4001, dtype=np.int64) * 200, L))})
+# full-size multi-wave batches (BASELINE configs[2] / configs[3] shapes): a strided + tail sample of windows against the reference
+import torch
+for tag, model, n, ns, rate, dt in (("configs[2] 100k x 400 model 2 fp64", 2, 100_000, 400, 400.0, np.float64), ("configs[3] per-GPU share 125k x 200 model 1 fp32 storage", 1, 125_000, 200, 200.0, np.float32),
+                                   ("125k x 200 model 1 fp64", 1, 125_000, 200, 200.0, np.float64)):
+    nd = 12_500
+    S, L = synth.make_windows(nd, ns, rate=rate, first_window=70_000)
+    Sx, Lx = S.astype(dt), L.astype(dt)
+    reps = n // nd
+    dS = torch.from_numpy(Sx).cuda().repeat(reps, 1, 1).contiguous(); dL = torch.from_numpy(Lx).cuda().repeat(reps, 1).contiguous()
+    got = preint.preintegrate(model, dS, dL, synth.SIGMAS, 0, ns=ns)
+    torch.cuda.synchronize()
+    sel = np.unique(np.r_[0:80, n // 2:n // 2 + 80, n - 200:n, np.arange(0, n, 997)])
+    g = got[torch.from_numpy(sel).cuda()].cpu().numpy().astype(np.float64)
+    src = sel % nd
+    ref = R.preintegrate(model, Sx[src].astype(np.float64), Lx[src].astype(np.float64), synth.SIGMAS, 0, ns=ns, nthreads=cores)
+    off = np.arange(len(sel) + 1, dtype=np.int64) * ns
+    report["cases"].append({"what": tag, "windows_in_batch": n, "windows_compared": int(len(sel)), "inputs": f"{nd} distinct windows tiled x{reps} on the device",
+                            "worst_error_over_compared_windows": field_errors(g, ref, model, window_band(S[src].reshape(-1, 7), off, L[src]))})
+    del dS, dL, got
 # factor evaluation, 5k chain, both models
 for model in (1, 2):
     S, L = synth.make_windows(4999, 20, first_window=9000)
