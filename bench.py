@@ -585,7 +585,7 @@ def main():
     if args.workload == "v1_10k_200" and not args.no_configs:
         extra = []
         k = max(3, min(args.steps, 10))
-        for name, distinct in (("v2_100k_400", 12_500), ("v1_1m_200_fp32", 12_500)):
+        for name, distinct in (("v2_100k_400", 5_000), ("v1_1m_200_fp32", 5_000)):
             try:
                 extra.append(compact(name, measure_preint(ctx, name, args, k, 3, distinct=distinct, e2e=(ctx.world == 1), cpu=False, clocks=False)))
             except Exception as ex:     # noqa: BLE001 -- reported in the line, never hidden

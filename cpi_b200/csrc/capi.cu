@@ -128,7 +128,7 @@ int preintegrate_dev(int model, int dtype, int64_t n_windows, const int64_t* sam
 extern "C" {
 
 const char* cpi_last_error(void) { return g_err.c_str(); }
-const char* cpi_version(void) { return "cpi_b200 0.1 (sm_100a)"; }
+const char* cpi_version(void) { return "cpi_b200 0.2 (sm_100a)"; }
 int cpi_record_doubles(int model) { return model == 1 ? CPI_REC_V1_DOUBLES : (model == 2 ? CPI_REC_V2_DOUBLES : CPI_EINVAL); }
 int64_t cpi_launch_count(void) { return g_launches.load(); }
 

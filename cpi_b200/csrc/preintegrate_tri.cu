@@ -177,9 +177,9 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah
             kGV[2] = TG2[0] * a0[0] + TG2[1] * a0[1] + TG2[2] * a0[2];
             // TV:  -W TV - GV + TT A_s[0,:]^T
             cross(xTV, w, kTV);
-            kTV[0] = (kTV[0] - xGV[0]) + (xTT[0] * a0[0] + xTT[1] * a0[1] + xTT[2] * a0[2]);
-            kTV[1] = (kTV[1] - xGV[1]) + (xTT[1] * a0[0] + t11 * a0[1] + t21 * a0[2]);
-            kTV[2] = (kTV[2] - xGV[2]) + (xTT[2] * a0[0] + t21 * a0[1] + t22 * a0[2]);
+            kTV[0] = fma(xTT[2], a0[2], fma(xTT[1], a0[1], fma(xTT[0], a0[0], kTV[0] - xGV[0])));      // one accumulation chain per entry
+            kTV[1] = fma(t21, a0[2], fma(t11, a0[1], fma(xTT[1], a0[0], kTV[1] - xGV[1])));
+            kTV[2] = fma(t22, a0[2], fma(t21, a0[1], fma(xTT[2], a0[0], kTV[2] - xGV[2])));
             T kTC[3], kCV[3];
             if (MODEL == 2) {
                 // GV += TG(start)^T C_s[0,:]^T ;  TV += TC C_s[0,:]^T
@@ -187,7 +187,7 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah
                 kGV[1] += G1s[0] * c0[0] + G1s[1] * c0[1] + G1s[2] * c0[2];
                 kGV[2] += G2s[0] * c0[0] + G2s[1] * c0[1] + G2s[2] * c0[2];
 #pragma unroll
-                for (int e = 0; e < 3; e++) kTV[e] += xTC[e] * c0[0] + TC1[e] * c0[1] + TC2[e] * c0[2];
+                for (int e = 0; e < 3; e++) kTV[e] = fma(TC2[e], c0[2], fma(TC1[e], c0[1], fma(xTC[e], c0[0], kTV[e])));
                 // TC:  -W TC - TG(start)^T  (column 0: minus row 0 of TG(start))
                 cross(xTC, w, kTC);
                 kTC[0] -= oTG[0]; kTC[1] -= G1s[0]; kTC[2] -= G2s[0];
@@ -305,9 +305,9 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah
 #pragma unroll
                     for (int e = 0; e < 3; e++) u[e] += u2[e];
                 }
-                negRt(Rs, u, m0);
+                (void)m0;
 #pragma unroll
-                for (int e = 0; e < 3; e++) kVP[e] = m0[e] + vv[e];
+                for (int e = 0; e < 3; e++) kVP[e] = fma(-Rs[6 + e], u[2], fma(-Rs[3 + e], u[1], fma(-Rs[e], u[0], vv[e])));   // VV_0 - (column e of R_s) . u
             }
             // PP:  VP + VP^T
             kPP[0] = xVP[0] + xVP[0]; kPP[1] = xVP[1] + shf(xVP[2], nx); kPP[2] = xVP[2] + shf(xVP[1], pv);

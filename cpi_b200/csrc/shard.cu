@@ -93,7 +93,11 @@ int cpi_comm_create(const void* id_in, int rank, int world, cpi_comm** out) {
     ncclUniqueId id;
     memcpy(&id, id_in, sizeof id);
     NC(g_nccl.CommInitRank(&c->comm, world, id, rank));
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // highest priority: when batch i's all-gather and batch i+1's kernel become runnable together, the collective's few CTAs must get
+    // their SM slots first -- the preintegration kernel fills every SM in one wave and would otherwise starve it until it ends
+    int prio_least = 0, prio_greatest = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
     CU(cudaEventCreateWithFlags(&c->kernel_done, cudaEventDisableTiming));
     for (int i = 0; i < cpi_comm::NBUF; i++) CU(cudaEventCreateWithFlags(&c->gathered[i], cudaEventDisableTiming));
     *out = c;
