@@ -390,10 +390,10 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
         e.record(stream)                     # force the lazy cudaEventCreate now
     # clock settle: the part idles at 120 MHz while the host generates inputs and needs ~20 ms of work (with a ~13 ms
     # P-state stall in it, measured) to reach its load clocks; keep it busy for >= 150 ms before the W warm-up steps
+    # (kernel only: this loop is time-bounded, so ranks may run different numbers of iterations -- no collective may be in it)
     t_settle = time.perf_counter()
-    k = 0
     while time.perf_counter() - t_settle < 0.15:
-        step(k); k += 1
+        preint.preintegrate(model, batches[0][0], batches[0][1], synth.SIGMAS, 0, ns=ns, out=gathers[0][rank], stream=stream)
         torch.cuda.synchronize()
     for i in range(warmup):
         step(i)
