@@ -560,6 +560,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configs appended to the default line")
+    ap.add_argument("--distinct", type=int, default=0, help="generate only this many distinct windows on the host and tile them on the device (0 = all distinct)")
     ap.add_argument("--no-clocks", action="store_true", help="debug: do not poll nvidia-smi during the timed region")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -579,7 +580,7 @@ def main():
                       "dtype": "f64", "data": "synthetic", "gpu_launches": 50})
             print(json.dumps(r), flush=True)
         return
-    out = measure_preint(ctx, args.workload, args, args.steps, args.warmup, e2e=True, cpu=True)
+    out = measure_preint(ctx, args.workload, args, args.steps, args.warmup, distinct=args.distinct or None, e2e=True, cpu=True)
 
     # ---- the other BASELINE configs, short runs, appended to the default line so that the driver's record carries them
     if args.workload == "v1_10k_200" and not args.no_configs:
