@@ -474,6 +474,22 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
         for _ in range(3):
             host_step()
         torch.cuda.synchronize()
+        # the floor of this box: a plain pinned cudaMemcpyAsync of the same input bytes (H2D) and output bytes (D2H), back to back
+        dprobe = torch.empty_like(hS, device=dev); oprobe = torch.empty((n, rd), dtype=tdt, device=dev)
+        for _ in range(2):
+            dprobe.copy_(hS, non_blocking=True); hO.copy_(oprobe, non_blocking=True)
+        torch.cuda.synchronize()
+        tp0 = time.perf_counter()
+        for _ in range(5):
+            dprobe.copy_(hS, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_ms = (time.perf_counter() - tp0) * 1e3 / 5
+        tp0 = time.perf_counter()
+        for _ in range(5):
+            hO.copy_(oprobe, non_blocking=True)
+        torch.cuda.synchronize()
+        d2h_ms = (time.perf_counter() - tp0) * 1e3 / 5
+        del dprobe, oprobe
         if world > 1:
             dist.barrier()
         ke = max(3, min(steps, 10))
@@ -488,7 +504,9 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
             e2e_ms = float(t.item())
         out["e2e"] = {"value": world * n / (e2e_ms * 1e-3), "unit": "windows/s", "ms_per_step": e2e_ms,
                       "h2d_bytes_per_step": int(hS.numel() * es + hL.numel() * es), "d2h_bytes_per_step": int(hO.numel() * es),
-                      "api": "cpi_preintegrate_batch_host (C ABI, pinned host buffers)"}
+                      "api": "cpi_preintegrate_batch_host (C ABI, pinned host buffers)",
+                      "pcie_floor": {"h2d_ms": h2d_ms, "h2d_gbs": hS.numel() * es / h2d_ms * 1e-6, "d2h_ms": d2h_ms,
+                                     "note": "plain pinned cudaMemcpyAsync of the same bytes on this box, measured in this run; the copies run full duplex, so H2D alone is the floor of the host path"}}
         if ctx.numa:
             out["e2e"]["host_numa"] = f"every rank bound to the NUMA node of its GPU (rank 0: node {ctx.numa['node']}, {ctx.numa['cpus']} cpus) before allocating its pinned buffers"
         del hS, hL, hO
