@@ -12,7 +12,14 @@
 
 namespace cpi {
 
-constexpr int FPB = 16;                 // factors per block (313 CTAs for a 5k chain: ~2 per SM, the launch is latency-sized)
+// Factors per block and threads per block.  The compute phase is one lane per factor and latency-bound (~2 k dependent instructions), so
+// what matters is how many CTAs an SM can hold while others stream out: 8 factors x 64 threads = 30 KB of tile at 255 registers ->
+// 4 CTAs per SM (round 1: 16 x 128 threads at 255 registers -> 2 per SM).  625 CTAs for a 5k chain: all resident in one wave.
+constexpr int FPB = 8;
+constexpr int FTHREADS = 64;
+#ifndef CPI_K3_MINB
+#define CPI_K3_MINB 4        /* resident CTAs per SM the register allocation aims at (4: 255 registers, no spills) */
+#endif
 constexpr int FTILE = 15 + 225 + 225;   // doubles per factor in the staging tile
 
 
@@ -45,7 +52,7 @@ CPI_DEV void putI(double* H, int r0, int c0, double s) {
 }
 
 template <int MODEL>
-__global__ void __launch_bounds__(128) k_factor_eval(const FactorParams p) {
+__global__ void __launch_bounds__(FTHREADS, CPI_K3_MINB) k_factor_eval(const FactorParams p) {
     extern __shared__ double tile[];
     const int tid = threadIdx.x;
     const int64_t f0 = (int64_t)blockIdx.x * FPB;
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(128) k_factor_eval(const FactorParams p) {
     }
     __syncthreads();
 
-    // coalesced stream-out: three contiguous ranges per CTA, 16 bytes per lane (f0 is a multiple of FPB = 16, so every range starts
+    // coalesced stream-out: three contiguous ranges per CTA, 16 bytes per lane (f0 is a multiple of FPB = 8, so every range starts
     // 16-byte aligned when the caller's arrays are; the last element of an odd-length range goes out as a single double)
     auto copy_out = [&](double* dst, const double* src, int n) {
         if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
@@ -352,8 +359,8 @@ cudaError_t factor_launch(int model, const FactorParams& p, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         if (dev < 64) configured[dev] = true;
     }
-    if (model == 1) k_factor_eval<1><<<grid, 128, smem, st>>>(p);
-    else k_factor_eval<2><<<grid, 128, smem, st>>>(p);
+    if (model == 1) k_factor_eval<1><<<grid, FTHREADS, smem, st>>>(p);
+    else k_factor_eval<2><<<grid, FTHREADS, smem, st>>>(p);
     return cudaGetLastError();
 }
 
