@@ -14,8 +14,10 @@ CASES = ("cam200", "real200", "real100", "real400", "synth200", "edge")
 MODES = [(1, 0), (1, 1), (2, 0), (2, 1), (2, 2), (2, 3)]
 # fp32-storage variant (dtype 32): no fp32 reference exists; gates = 2x the worst error observed on B200 against the fp64 oracle on the
 # same float-rounded inputs.  R/alpha/beta/J/H: fp64 arithmetic, float output rounding; P: fp32 RK4.
-FP32_GATES = {1: dict(R=2e-7, alpha=2e-7, beta=2e-7, J_q=2e-7, J_a=2e-7, J_b=2e-7, H_a=2e-7, H_b=2e-7, P=2e-4, P_block=2e-4),
-              2: dict(R=2e-7, alpha=2e-7, beta=2e-7, J_q=5e-6, J_a=5e-6, J_b=5e-6, H_a=5e-6, H_b=5e-6, O_a=5e-6, O_b=5e-6, P=2e-4, P_block=2e-4)}
+FP32_GATES = {1: dict(R=1.5e-7, alpha=1.5e-7, beta=1.5e-7, J_q=1.5e-7, J_a=1.5e-7, J_b=1.5e-7, H_a=1.5e-7, H_b=1.5e-7, P=6e-7, P_block=6e-7),
+              2: dict(R=1.5e-7, alpha=1.5e-7, beta=1.5e-7, J_q=1.5e-7, J_a=1.5e-7, J_b=1.5e-7, H_a=1.5e-7, H_b=1.5e-7, O_a=1.5e-7, O_b=1.5e-7, P=1e-6, P_block=1e-6)}
+# observed on B200 (profiles/r02_parity_vs_reference.json), model 1: R 6.4e-8, alpha/beta 5.1e-8, J/H 5.5e-8, P 2.3e-7, worst 3x3 block of P 2.9e-7:
+# with the state accumulated in fp64 even the fp32 variant meets the north_star's 1e-6 on P, block-wise.
 
 
 def _inputs(G, name, flags):
@@ -239,16 +241,15 @@ def test_fp32_storage_variant(cuda, oracle, model, flags):
     assert got.dtype == np.float32 and np.all(np.isfinite(got))
     ref = oracle.preintegrate(model, S32.astype(np.float64), L32.astype(np.float64), synth.SIGMAS, flags, ns=ns, nthreads=16)
     g64 = got.astype(np.float64)
-    worst = {}
-    for name, (a, b) in dict(R=(4, 13), alpha=(13, 16), beta=(16, 19), J_q=(20, 29), J_a=(29, 38), J_b=(38, 47), H_a=(47, 56), H_b=(56, 65), P=(65, 290)).items():
-        num = np.linalg.norm(g64[:, a:b] - ref[:, a:b], axis=1); den = np.maximum(np.linalg.norm(ref[:, a:b], axis=1), 1e-30)
-        worst[name] = float(np.max(num / den))
+    from parity import fp32_errors
+    worst = fp32_errors(got, ref)
     print(model, flags, {k: f"{v:.1e}" for k, v in worst.items()})
-    for name in ("R", "alpha", "beta"):
-        assert worst[name] <= 5e-7, (name, worst[name])          # output rounding only: these are computed in fp64
-    for name in ("J_q", "J_b", "H_a", "H_b"):
-        assert worst[name] <= 5e-6, (name, worst[name])          # model 2 reads them out of Phi, whose theta-row stage values pass through float slots
-    assert worst["P"] <= 2e-4, worst["P"]                            # fp32 RK4 over 200 steps
+    # the imu_avg / analytic modes run on the round-1 lane-per-window kernels (float tile, float state): their P gate is the round-1 one
+    legacy = bool(flags)
+    for k, gate in FP32_GATES[model].items():
+        g = gate if not (legacy and k in ("P", "P_block")) else 2e-4
+        g = g if not (legacy and model == 2 and k in ("J_q", "J_a", "J_b", "H_a", "H_b", "O_a", "O_b")) else 5e-6
+        assert worst[k] <= g, (k, worst[k], g)
     P = g64[:, 65:290].reshape(n, 15, 15)
     assert np.array_equal(P, P.transpose(0, 2, 1)) and np.all(P[:, 0:6, 9:12] == 0)
     # device-pointer entry point, float tensors
