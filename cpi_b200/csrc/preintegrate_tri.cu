@@ -217,6 +217,88 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah
 #endif
     }
     CPI_FENCE();
+#ifdef CPI_TRI_FUSE12
+    {   // ---- groups 1b + 2 fused: AV, VV, TP, GP, AP, VP, PP in ONE stage loop (AV / VV never go through the slots)
+        T xAV[3], xVV[3], sAV[3], sVV[3], oAV[3], oVV[3];
+        T xTP[3], xGP[3], xAP[3], xVP[3], oTP[3], oGP[3], oAP[3], oVP[3];
+        T sTP[3], sGP[3], sAP[3], sVP[3], sPP[3];
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            oAV[e] = (T)P.AV[e]; oVV[e] = (T)P.VV[e]; xAV[e] = oAV[e]; xVV[e] = oVV[e];
+            oTP[e] = (T)P.TP[e]; oGP[e] = (T)P.GP[e]; oAP[e] = (T)P.AP[e]; oVP[e] = (T)P.VP[e];
+            xTP[e] = oTP[e]; xGP[e] = oGP[e]; xAP[e] = oAP[e]; xVP[e] = oVP[e];
+        }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const T* Rs = (s == 0) ? R : (s == 3 ? R1 : Rm);
+            const T rc[3] = {Rs[0], Rs[3], Rs[6]};
+            T tv[3], gv[3], cv[3];
+#pragma unroll
+            for (int e = 0; e < 3; e++) { tv[e] = SLT(s * NS + e); gv[e] = SLT(s * NS + 3 + e); if (MODEL == 2) cv[e] = SLT(s * NS + 12 + e); }
+            const T pa_s = (s == 0) ? paa : fma(q_ab, (s == 3 ? dt : hdt), paa);
+            T kAV[3], kVV[3], kTP[3], kVP[3], kPP[3];
+#pragma unroll
+            for (int e = 0; e < 3; e++) kAV[e] = -(pa_s * rc[e]);
+            {   // VV:  M + M^T + q_a I,  M[:,0] = -R_s^T (a x TV_0 + AV_0 (+ g_tau x CV_0))
+                T u[3], m0[3];
+                cross(ah, tv, u);
+#pragma unroll
+                for (int e = 0; e < 3; e++) u[e] += xAV[e];
+                if (MODEL == 2) {
+                    T u2[3];
+                    cross(gt, cv, u2);
+#pragma unroll
+                    for (int e = 0; e < 3; e++) u[e] += u2[e];
+                }
+                negRt(Rs, u, m0);
+                const T m01 = shf(m0[2], nx), m02 = shf(m0[1], pv);
+                kVV[0] = m0[0] + m0[0] + q_a; kVV[1] = m0[1] + m01; kVV[2] = m0[2] + m02;
+            }
+            // TP:  -W TP - GP + TV
+            cross(xTP, w, kTP);
+#pragma unroll
+            for (int e = 0; e < 3; e++) kTP[e] = (kTP[e] - xGP[e]) + tv[e];
+            {   // VP:  A_s TP_0 + B_s AP_0 (+ C_s CP_0) + VV_0
+                T u[3];
+                cross(ah, xTP, u);
+#pragma unroll
+                for (int e = 0; e < 3; e++) u[e] += xAP[e];
+                if (MODEL == 2) {
+                    T cp[3], u2[3];
+#pragma unroll
+                    for (int e = 0; e < 3; e++) cp[e] = (s == 0) ? oTP[e] : fma((T)SLT((s - 1) * NS + 12 + e), CN(s - 1), oTP[e]);
+                    cross(gt, cp, u2);
+#pragma unroll
+                    for (int e = 0; e < 3; e++) u[e] += u2[e];
+                }
+#pragma unroll
+                for (int e = 0; e < 3; e++) kVP[e] = fma(-Rs[6 + e], u[2], fma(-Rs[3 + e], u[1], fma(-Rs[e], u[0], xVV[e])));
+            }
+            kPP[0] = xVP[0] + xVP[0]; kPP[1] = xVP[1] + shf(xVP[2], nx); kPP[2] = xVP[2] + shf(xVP[1], pv);
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                sTP[e] = KSUM(sTP[e], kTP[e], s); sGP[e] = KSUM(sGP[e], gv[e], s); sAP[e] = KSUM(sAP[e], xAV[e], s);
+                sVP[e] = KSUM(sVP[e], kVP[e], s); sPP[e] = KSUM(sPP[e], kPP[e], s);
+                sAV[e] = KSUM(sAV[e], kAV[e], s); sVV[e] = KSUM(sVV[e], kVV[e], s);
+                if (s < 3) {
+                    xTP[e] = fma(kTP[e], CN(s), oTP[e]); xGP[e] = fma(gv[e], CN(s), oGP[e]); xAP[e] = fma(xAV[e], CN(s), oAP[e]);
+                    xVP[e] = fma(kVP[e], CN(s), oVP[e]);
+                    xAV[e] = fma(kAV[e], CN(s), oAV[e]); xVV[e] = fma(kVV[e], CN(s), oVV[e]);
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            P.AV[e] = fma((double)dt6, (double)sAV[e], P.AV[e]); P.VV[e] = fma((double)dt6, (double)sVV[e], P.VV[e]);
+            P.TP[e] = fma((double)dt6, (double)sTP[e], P.TP[e]); P.GP[e] = fma((double)dt6, (double)sGP[e], P.GP[e]);
+            P.AP[e] = fma((double)dt6, (double)sAP[e], P.AP[e]); P.VP[e] = fma((double)dt6, (double)sVP[e], P.VP[e]);
+            P.PP[e] = fma((double)dt6, (double)sPP[e], P.PP[e]);
+        }
+    }
+    CPI_FENCE();
+}
+
+#else
     {   // ---- group 1b: AV, VV (need TV's stage values)
         T xAV[3], xVV[3], sAV[3], sVV[3], oAV[3], oVV[3];
 #ifdef CPI_TRI_PSMEM
@@ -335,6 +417,7 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah
     CPI_FENCE();
 }
 
+#endif
 // D v  with  D = I - a [w x] + b [w x]^2 :   v - a (w x v) + b (w x (w x v));  second result with (a2, b2) on the same cross products
 CPI_DEV void rot_col2(double a, double b, double a2, double b2, const double* w, const double* v, double* o, double* o2) {
     double t[3], u[3];
