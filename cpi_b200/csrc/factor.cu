@@ -13,12 +13,12 @@
 namespace cpi {
 
 // Factors per block and threads per block.  The compute phase is one lane per factor and latency-bound (~2 k dependent instructions), so
-// what matters is how many CTAs an SM can hold while others stream out: 8 factors x 64 threads = 30 KB of tile at 255 registers ->
-// 4 CTAs per SM (round 1: 16 x 128 threads at 255 registers -> 2 per SM).  625 CTAs for a 5k chain: all resident in one wave.
+// what matters is how many CTAs an SM can hold while others stream out: 8 factors x 64 threads = 30 KB of tile at 168 registers ->
+// 6 CTAs per SM (round 1: 16 x 128 threads at 255 registers -> 2 per SM).  625 CTAs for a 5k chain: all resident in one wave.
 constexpr int FPB = 8;
 constexpr int FTHREADS = 64;
 #ifndef CPI_K3_MINB
-#define CPI_K3_MINB 4        /* resident CTAs per SM the register allocation aims at (4: 255 registers, no spills) */
+#define CPI_K3_MINB 6        /* resident CTAs per SM the register allocation aims at: 6 (168 registers, ~400 B of spills) measured faster than 4 (255, none): 789 vs 671 M factors/s at 1M */
 #endif
 constexpr int FTILE = 15 + 225 + 225;   // doubles per factor in the staging tile
 
