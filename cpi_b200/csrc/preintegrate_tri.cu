@@ -34,7 +34,7 @@ constexpr int TRI_WPW = 10;                 // windows per warp (lanes 30, 31 id
 // distribution by the hardware block scheduler (10 000 windows = 1 000 CTAs over 148 SMs: 6 or 7 per SM, one wave), (b) kernels of
 // different streams co-residing on an SM, which is what lets the host entry point pipeline a batch in many small chunks, and (c) a
 // finer tail on multi-wave batches.  Up to 8 CTAs per SM: 255 registers x 32 lanes x 8 = the register file; shared memory per CTA is
-// kept under 220 KB / 8 (model 2 in fp64: 7 CTAs per SM).
+// kept under 220 KB / 8 for every instantiation (model 1 fp64: 21 KB, model 2 fp64: 24 KB).
 template <int MODEL, class T> struct TriNT { static constexpr int NT = 32; };
 constexpr int TRI_NBUF = 3;                 // 128-byte chunk buffers per window (TMA ring)
 constexpr int TRI_BUF_STRIDE = TRI_NBUF * 128 + 16;   // bytes of sample staging per window, + 16 B pad (bank spread; 16-B aligned for TMA)
@@ -53,7 +53,11 @@ template <class T> CPI_DEV void gather_cols(const T* V, int nx, int pv, T* X1, T
 // RK4 stage values handed from the (theta|v)-column group to the p-column group through LANE-PRIVATE shared memory
 // slots, [entry][thread]: TV, GV, AV, VV (model 2: + CV) for the four stages.
 template <int MODEL> struct TriL {
-    static constexpr int NSL = (MODEL == 1 ? 12 : 15) * 4;
+#ifndef CPI_TRI_UNFUSED12
+    static constexpr int NSL = (MODEL == 1 ? 6 : 9) * 4;        // TV, GV (+ CV) for the four stages
+#else
+    static constexpr int NSL = (MODEL == 1 ? 12 : 15) * 4;      // + AV, VV in the split cascade
+#endif
     // front state parked in lane-private smem during the covariance step: bw, ba, alpha, beta, then
     //   model 1: J_q, J_a, J_b, H_a, H_b (own columns)      model 2: g_k and the own columns of the 7 non-trivial Discrete_J_b blocks
     static constexpr int NFS = (MODEL == 1) ? 23 : 32;
@@ -77,7 +81,7 @@ template <int MODEL, class T> struct TriSmem {
 #ifndef CPI_TRI_PSMEM
 static_assert(TriSmem<1, double>::bytes <= 28160 - 1024 && TriSmem<1, float>::bytes <= 28160 - 1024 && TriSmem<2, float>::bytes <= 28160 - 1024,
               "8 CTAs per SM need <= 220 KB / 8 of shared memory each (incl. 1 KB the system reserves per CTA)");
-static_assert(TriSmem<2, double>::bytes <= 32182 - 1024, "model 2 fp64: 7 CTAs per SM");
+static_assert(TriSmem<2, double>::bytes <= 32182 - 1024, "model 2 fp64 (split cascade: 7 CTAs per SM)");
 #endif
 
 #define SLT(e) sl[(e) * NT]
@@ -114,7 +118,13 @@ template <int MODEL, int NT, class T>
 CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah, const T* gt, const T* R, const T* Rm, const T* R1, T pgg, T paa, T dt, T dt6,
                           T q_w, T q_wb, T q_a, T q_ab, int nx, int pv) {
     const T hdt = dt * T(0.5);
-    constexpr int NS = (MODEL == 1) ? 12 : 15;            // slot entries per stage
+#ifndef CPI_TRI_UNFUSED12
+    constexpr int NS = (MODEL == 1) ? 6 : 9;              // slot entries per stage: TV, GV (+ CV)
+    constexpr int SL_CV = 6;
+#else
+    constexpr int NS = (MODEL == 1) ? 12 : 15;            // slot entries per stage: TV, GV, AV, VV (+ CV)
+    constexpr int SL_CV = 12;
+#endif
     // Model 2 (CpiV2.h:326-443): the clone rows c of P_big are re-initialised from the theta rows at every step (B_k), so within a
     // step  P_cg = TG(start), P_cc = TT(start), P_ca = 0  are constant and only three transient blocks evolve:
     //     TC = P_theta,c  (starts as TT):  TC' = -W TC - TG(start)^T            [needs nothing cross-lane; TV and CV need all of it]
@@ -146,7 +156,7 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah
             const T t11 = shf(xTT[0], nx), t21 = shf(xTT[1], nx), t22 = shf(xTT[0], pv);
             // stage values the later groups need
 #pragma unroll
-            for (int e = 0; e < 3; e++) { SLT(s * NS + e) = xTV[e]; SLT(s * NS + 3 + e) = xGV[e]; if (MODEL == 2) SLT(s * NS + 12 + e) = xCV[e]; }
+            for (int e = 0; e < 3; e++) { SLT(s * NS + e) = xTV[e]; SLT(s * NS + 3 + e) = xGV[e]; if (MODEL == 2) SLT(s * NS + SL_CV + e) = xCV[e]; }
             const T pg_s = (s == 0) ? pgg : fma(q_wb, (s == 3 ? dt : hdt), pgg);
             T kTG[3], kTT[3], kGV[3], kTV[3];
             T c0[3], TC1[3], TC2[3];
@@ -217,7 +227,7 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah
 #endif
     }
     CPI_FENCE();
-#ifdef CPI_TRI_FUSE12
+#ifndef CPI_TRI_UNFUSED12      /* default: groups 1b and 2 fused (measured +6..8 % over the split cascade, which stays for A/B runs) */
     {   // ---- groups 1b + 2 fused: AV, VV, TP, GP, AP, VP, PP in ONE stage loop (AV / VV never go through the slots)
         T xAV[3], xVV[3], sAV[3], sVV[3], oAV[3], oVV[3];
         T xTP[3], xGP[3], xAP[3], xVP[3], oTP[3], oGP[3], oAP[3], oVP[3];
@@ -234,7 +244,7 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah
             const T rc[3] = {Rs[0], Rs[3], Rs[6]};
             T tv[3], gv[3], cv[3];
 #pragma unroll
-            for (int e = 0; e < 3; e++) { tv[e] = SLT(s * NS + e); gv[e] = SLT(s * NS + 3 + e); if (MODEL == 2) cv[e] = SLT(s * NS + 12 + e); }
+            for (int e = 0; e < 3; e++) { tv[e] = SLT(s * NS + e); gv[e] = SLT(s * NS + 3 + e); if (MODEL == 2) cv[e] = SLT(s * NS + SL_CV + e); }
             const T pa_s = (s == 0) ? paa : fma(q_ab, (s == 3 ? dt : hdt), paa);
             T kAV[3], kVV[3], kTP[3], kVP[3], kPP[3];
 #pragma unroll
@@ -266,7 +276,7 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah
                 if (MODEL == 2) {
                     T cp[3], u2[3];
 #pragma unroll
-                    for (int e = 0; e < 3; e++) cp[e] = (s == 0) ? oTP[e] : fma((T)SLT((s - 1) * NS + 12 + e), CN(s - 1), oTP[e]);
+                    for (int e = 0; e < 3; e++) cp[e] = (s == 0) ? oTP[e] : fma((T)SLT((s - 1) * NS + SL_CV + e), CN(s - 1), oTP[e]);
                     cross(gt, cp, u2);
 #pragma unroll
                     for (int e = 0; e < 3; e++) u[e] += u2[e];
@@ -328,7 +338,7 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah
                 if (MODEL == 2) {                             // + C_s CV_0 = -R_s^T (g_tau x CV_0)
                     T cv[3], u2[3];
 #pragma unroll
-                    for (int e = 0; e < 3; e++) cv[e] = SLT(s * NS + 12 + e);
+                    for (int e = 0; e < 3; e++) cv[e] = SLT(s * NS + SL_CV + e);
                     cross(gt, cv, u2);
 #pragma unroll
                     for (int e = 0; e < 3; e++) u[e] += u2[e];
@@ -382,7 +392,7 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah
                 if (MODEL == 2) {                             // + C_s CP_0,  CP_s = TP(start) + CN(s-1) CV_{s-1}
                     T cp[3], u2[3];
 #pragma unroll
-                    for (int e = 0; e < 3; e++) cp[e] = (s == 0) ? oTP[e] : fma((T)SLT((s - 1) * NS + 12 + e), CN(s - 1), oTP[e]);
+                    for (int e = 0; e < 3; e++) cp[e] = (s == 0) ? oTP[e] : fma((T)SLT((s - 1) * NS + SL_CV + e), CN(s - 1), oTP[e]);
                     cross(gt, cp, u2);
 #pragma unroll
                     for (int e = 0; e < 3; e++) u[e] += u2[e];
