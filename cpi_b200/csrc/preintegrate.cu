@@ -1235,14 +1235,13 @@ template <class T>
 static cudaError_t launch_ws(const PreintParams& p0, int num_sms, cudaStream_t st) {
     PreintParams p = p0;
     auto kern = k_preintegrate_ws<T>;
-    static bool configured = false;
-    static int configured_dev = -1;
+    static bool configured[64] = {false};     // per device (the attribute is sticky per device context); the worst a race can do is set it twice
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!configured || configured_dev != dev) {
+    if (dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileWS<T>::bytes);
         if (e != cudaSuccess) return e;
-        configured = true; configured_dev = dev;
+        if (dev < 64) configured[dev] = true;
     }
     const int cap = TileWS<T>::S;
     const int64_t need = (p.n_windows + num_sms - 1) / num_sms;
@@ -1257,14 +1256,13 @@ static cudaError_t launch_ws(const PreintParams& p0, int num_sms, cudaStream_t s
 template <int MODEL, bool AVG, bool ANALYTIC, class T>
 static cudaError_t launch_one(const PreintParams& p, int grid, int block, cudaStream_t st) {
     auto kern = k_preintegrate<MODEL, AVG, ANALYTIC, T>;
-    static bool configured = false;     // per instantiation; the attribute is sticky per device context
-    static int configured_dev = -1;
+    static bool configured[64] = {false};     // per instantiation and device; the attribute is sticky per device context
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!configured || configured_dev != dev) {
+    if (dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes<MODEL, T>());
         if (e != cudaSuccess) return e;
-        configured = true; configured_dev = dev;
+        if (dev < 64) configured[dev] = true;
     }
     kern<<<grid, block, tile_bytes<MODEL, T>(), st>>>(p);
     return cudaGetLastError();

@@ -38,8 +38,9 @@ constexpr int TRI_WPW = 10;                 // windows per warp (lanes 30, 31 id
 template <int MODEL, class T> struct TriNT { static constexpr int NT = 32; };
 constexpr int TRI_NBUF = 3;                 // 128-byte chunk buffers per window (TMA ring)
 constexpr int TRI_BUF_STRIDE = TRI_NBUF * 128 + 16;   // bytes of sample staging per window, + 16 B pad (bank spread; 16-B aligned for TMA)
-// doubles per window of pre-pass scalars: 3 samples x 16 (model 1: 15 used) or 3 x 10 (model 2: 9 used), padded to an odd stride (bank spread)
-template <int MODEL> struct TriSC { static constexpr int PER = (MODEL == 1) ? 16 : 10, STRIDE = 3 * PER + 1 + (MODEL == 1 ? 2 : 0); };
+// doubles per window of pre-pass scalars: 3 samples x 16 (model 1: 15 used) or 3 x 10 (model 2: 9 used), padded for bank spread
+// (strides are multiples of 2 doubles so that the sets can be moved with 16-byte accesses: 50 / 34 doubles = a 4-bank shift per window)
+template <int MODEL> struct TriSC { static constexpr int PER = (MODEL == 1) ? 16 : 10, STRIDE = (MODEL == 1) ? 50 : 34; };
 
 template <class T> CPI_DEV T shf(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
@@ -246,7 +247,7 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah
 #pragma unroll
             for (int e = 0; e < 3; e++) { tv[e] = SLT(s * NS + e); gv[e] = SLT(s * NS + 3 + e); if (MODEL == 2) cv[e] = SLT(s * NS + SL_CV + e); }
             const T pa_s = (s == 0) ? paa : fma(q_ab, (s == 3 ? dt : hdt), paa);
-            T kAV[3], kVV[3], kTP[3], kVP[3], kPP[3];
+            T kAV[3], kVV[3], kTP[3], kVP[3];
 #pragma unroll
             for (int e = 0; e < 3; e++) kAV[e] = -(pa_s * rc[e]);
             {   // VV:  M + M^T + q_a I,  M[:,0] = -R_s^T (a x TV_0 + AV_0 (+ g_tau x CV_0))
@@ -284,11 +285,12 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah
 #pragma unroll
                 for (int e = 0; e < 3; e++) kVP[e] = fma(-Rs[6 + e], u[2], fma(-Rs[3 + e], u[1], fma(-Rs[e], u[0], xVV[e])));
             }
-            kPP[0] = xVP[0] + xVP[0]; kPP[1] = xVP[1] + shf(xVP[2], nx); kPP[2] = xVP[2] + shf(xVP[1], pv);
+            // PP' = VP + VP^T has no dependants: only the own-column integral of VP is accumulated here (P.PP holds Q = int VP[:,0]);
+            // the transpose is added ONCE per window, when the record is written (PP = Q + Q^T), instead of one exchange per stage
 #pragma unroll
             for (int e = 0; e < 3; e++) {
                 sTP[e] = KSUM(sTP[e], kTP[e], s); sGP[e] = KSUM(sGP[e], gv[e], s); sAP[e] = KSUM(sAP[e], xAV[e], s);
-                sVP[e] = KSUM(sVP[e], kVP[e], s); sPP[e] = KSUM(sPP[e], kPP[e], s);
+                sVP[e] = KSUM(sVP[e], kVP[e], s); sPP[e] = KSUM(sPP[e], xVP[e], s);
                 sAV[e] = KSUM(sAV[e], kAV[e], s); sVV[e] = KSUM(sVV[e], kVV[e], s);
                 if (s < 3) {
                     xTP[e] = fma(kTP[e], CN(s), oTP[e]); xGP[e] = fma(gv[e], CN(s), oGP[e]); xAP[e] = fma(xAV[e], CN(s), oAP[e]);
@@ -628,7 +630,8 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
             }
             constexpr int NSC = (MODEL == 1) ? (int)SC_N : (int)SC_D1;
 #pragma unroll
-            for (int e = 0; e < NSC; e++) sc[c * TriSC<MODEL>::PER + e] = v[e];
+            for (int e = 0; e < (NSC + 1) / 2; e++)           // 16-byte stores
+                reinterpret_cast<double2*>(sc + c * TriSC<MODEL>::PER)[e] = make_double2(v[2 * e], 2 * e + 1 < SC_N ? v[2 * e + 1] : 0.0);
         }
         __syncwarp();
 
@@ -654,7 +657,13 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
             }
             DT += dt;                                                // CpiV1.h:69 (before the dt == 0 return)
             if (kLoadOnly) { DT += wm[0] + wm[1] + wm[2] + am[0] + am[1] + am[2]; continue; }
-            const double* scj = sc + j * TriSC<MODEL>::PER;
+            double scj[SC_N];                                        // this sample's scalar set, 16-byte loads (same address in the trio: broadcast)
+            {
+                constexpr int NLD = (MODEL == 1) ? (int)SC_N : (int)SC_D1;
+                const double2* s2 = reinterpret_cast<const double2*>(sc + j * TriSC<MODEL>::PER);
+#pragma unroll
+                for (int e = 0; e < (NLD + 1) / 2; e++) { const double2 t2 = s2[e]; scj[2 * e] = t2.x; if (2 * e + 1 < SC_N) scj[2 * e + 1] = t2.y; }
+            }
             const double a1 = scj[SC_A1], b1 = scj[SC_B1], a2 = scj[SC_A2], b2 = scj[SC_B2];
             const double f1 = scj[SC_F1], f2 = scj[SC_F2], f3 = scj[SC_F3], f4 = scj[SC_F4], dt6 = kCovOnly ? dt / 6.0 : scj[SC_DT6];
 
@@ -848,7 +857,11 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
     double sTT[3], sVV[3], sPP[3];
     sTT[0] = P.TT[0]; sTT[1] = 0.5 * (P.TT[1] + shf(P.TT[2], nx)); sTT[2] = 0.5 * (P.TT[2] + shf(P.TT[1], pv));
     sVV[0] = P.VV[0]; sVV[1] = 0.5 * (P.VV[1] + shf(P.VV[2], nx)); sVV[2] = 0.5 * (P.VV[2] + shf(P.VV[1], pv));
+#ifndef CPI_TRI_UNFUSED12
+    sPP[0] = P.PP[0] + P.PP[0]; sPP[1] = P.PP[1] + shf(P.PP[2], nx); sPP[2] = P.PP[2] + shf(P.PP[1], pv);     // PP = Q + Q^T (exactly symmetric: a + b == b + a)
+#else
     sPP[0] = P.PP[0]; sPP[1] = 0.5 * (P.PP[1] + shf(P.PP[2], nx)); sPP[2] = 0.5 * (P.PP[2] + shf(P.PP[1], pv));
+#endif
     if (!active) return;
     constexpr int RD = (MODEL == 1) ? CPI_REC_V1_DOUBLES : CPI_REC_V2_DOUBLES;
     T* rec = reinterpret_cast<T*>(p.out) + win * (int64_t)RD;

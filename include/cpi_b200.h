@@ -91,7 +91,9 @@ extern "C" {
  *                  see DESIGN.md for the mixed-precision rule)
  *   sample_offsets device int64[n_windows+1], entry index (not bytes) of each window's first entry in `samples`;
  *                  or NULL for uniform windows of `ns_uniform` steps laid out back to back.
- *                  Window w has  steps = offsets[w+1]-offsets[w]  (minus 1 if CPI_FLAG_IMU_AVG).
+ *                  Window w has  steps = offsets[w+1]-offsets[w]  (minus 1 if CPI_FLAG_IMU_AVG).  Device-resident offsets cannot
+ *                  be validated by this entry point: a decreasing pair yields a zero-step window (the _host variant checks
+ *                  its host copy and returns CPI_EINVAL instead).
  *   samples        device, CPI_SAMPLE_DOUBLES per entry.  The kernels stage every window's stream with 128-byte TMA bulk reads that
  *                  start at the 16-byte boundary at or below the window's first entry: `samples` must be 16-byte aligned (any
  *                  cudaMalloc / torch allocation is), so that no read begins before the buffer; reads never extend past the
