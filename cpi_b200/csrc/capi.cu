@@ -340,15 +340,16 @@ int cpi_imu_factor_whiten_batch(int model, int64_t n_factors, const double* reco
 }
 
 int cpi_imu_chain_assemble(int64_t n_factors, const double* G11, const double* G12, const double* G22, const double* g1, const double* g2, double lambda,
-                           const double* prior_info0, const double* prior_rhs0, double* D, double* E, double* rhs, void* stream) {
+                           int diagonal_damping, const double* prior_info0, const double* prior_rhs0, double* D, double* E, double* rhs, void* stream) {
     if (n_factors < 0) return fail(CPI_EINVAL, "negative count");
     if (n_factors > 0 && (!G11 || !G12 || !G22 || !g1 || !g2 || !E)) return fail(CPI_EINVAL, "null pointer argument");
     if (!D || !rhs) return fail(CPI_EINVAL, "null pointer argument");
     if (n_factors >= 2147483647) return fail(CPI_EINVAL, "chain too long");
+    if (!(lambda >= 0.0)) return fail(CPI_EINVAL, "lambda must be >= 0 (got %g)", lambda);
     DevInfo d;
     int rc = device_info(d);
     if (rc) return rc;
-    CU(cpi::chain_assemble_launch(n_factors, G11, G12, G22, g1, g2, lambda, prior_info0, prior_rhs0, D, E, rhs, (cudaStream_t)stream));
+    CU(cpi::chain_assemble_launch(n_factors, G11, G12, G22, g1, g2, lambda, diagonal_damping != 0, prior_info0, prior_rhs0, D, E, rhs, (cudaStream_t)stream));
     g_launches += 1;
     return CPI_OK;
 }

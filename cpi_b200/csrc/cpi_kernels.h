@@ -42,7 +42,7 @@ cudaError_t hessian_launch(int rd, int64_t n, const double* records, const doubl
                            double* G11, double* G12, double* G22, double* g1, double* g2, double* f, cudaStream_t st);
 cudaError_t whiten_launch(int rd, int64_t n, const double* records, const double* e, const double* H1, const double* H2, double* A1, double* A2, double* b, cudaStream_t st);
 cudaError_t chain_assemble_launch(int64_t nf, const double* G11, const double* G12, const double* G22, const double* g1, const double* g2, double lambda,
-                                  const double* prior_info, const double* prior_rhs, double* D, double* E, double* rhs, cudaStream_t st);
+                                  int diagonal_damping, const double* prior_info, const double* prior_rhs, double* D, double* E, double* rhs, cudaStream_t st);
 int64_t chain_solve_workspace_bytes(int64_t n_states);
 cudaError_t chain_solve_launch(int64_t n_states, const double* D, const double* E, const double* b, double* x, double* ws, cudaStream_t st, int* launches);
 cudaError_t retract_launch(int64_t n, const double* states, const double* xi, double* out, cudaStream_t st);

@@ -103,15 +103,17 @@ __global__ void __launch_bounds__(128) k_factor_whiten(int64_t n, int rd, const 
 }
 
 // ---- chain assembly ---------------------------------------------------------------------------------------------------------------
-// Factor f links states f and f+1:  D[k] = G22[k-1] + G11[k] + lambda I (+ prior on x_0),  E[k] = G12[k] (block (k, k+1)),  rhs[k] = g2[k-1] + g1[k]
+// Factor f links states f and f+1:  D[k] = G22[k-1] + G11[k] (+ prior on x_0) + damping,  E[k] = G12[k] (block (k, k+1)),  rhs[k] = g2[k-1] + g1[k].
+// Damping as in GTSAM's LevenbergMarquardtParams: lambda I, or with diagonalDamping lambda * clamp(diag, minDiagonal 1e-6, maxDiagonal 1e32).
 __global__ void k_chain_assemble(int64_t nf, const double* G11, const double* G12, const double* G22, const double* g1, const double* g2, double lambda,
-                                 const double* prior_info, const double* prior_rhs, double* D, double* E, double* rhs) {
+                                 int diagonal_damping, const double* prior_info, const double* prior_rhs, double* D, double* E, double* rhs) {
     const int64_t k = blockIdx.x;                                  // state index 0..nf
     for (int t = threadIdx.x; t < 225; t += blockDim.x) {
-        double d = (t % 16 == 0) ? lambda : 0.0;                   // t = r + 15 c: diagonal when r == c  <=>  t % 16 == 0
+        double d = 0.0;
         if (k > 0) d += G22[(k - 1) * 225 + t];
         if (k < nf) { d += G11[k * 225 + t]; E[k * 225 + t] = G12[k * 225 + t]; }
         if (k == 0 && prior_info) d += prior_info[t];
+        if (t % 16 == 0) d += diagonal_damping ? lambda * fmin(fmax(d, 1e-6), 1e32) : lambda;     // t = r + 15 c: diagonal when r == c  <=>  t % 16 == 0
         D[k * 225 + t] = d;
     }
     for (int t = threadIdx.x; t < 15; t += blockDim.x) {
@@ -249,8 +251,8 @@ cudaError_t whiten_launch(int rd, int64_t n, const double* records, const double
 }
 
 cudaError_t chain_assemble_launch(int64_t nf, const double* G11, const double* G12, const double* G22, const double* g1, const double* g2, double lambda,
-                                  const double* prior_info, const double* prior_rhs, double* D, double* E, double* rhs, cudaStream_t st) {
-    k_chain_assemble<<<(int)(nf + 1), 128, 0, st>>>(nf, G11, G12, G22, g1, g2, lambda, prior_info, prior_rhs, D, E, rhs);
+                                  int diagonal_damping, const double* prior_info, const double* prior_rhs, double* D, double* E, double* rhs, cudaStream_t st) {
+    k_chain_assemble<<<(int)(nf + 1), 128, 0, st>>>(nf, G11, G12, G22, g1, g2, lambda, diagonal_damping, prior_info, prior_rhs, D, E, rhs);
     return cudaGetLastError();
 }
 

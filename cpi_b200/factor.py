@@ -121,9 +121,10 @@ def factor_whiten(model, records, e, H1, H2, stream=None):
     return tuple(t.cpu().numpy() for t in out) if host else out
 
 
-def chain_assemble(G11, G12, G22, g1, g2, lam=0.0, prior_info0=None, prior_rhs0=None, stream=None):
+def chain_assemble(G11, G12, G22, g1, g2, lam=0.0, prior_info0=None, prior_rhs0=None, stream=None, diagonal_damping=False):
     """Block-tridiagonal normal equations of the chain x_0 .. x_n from the per-factor information blocks (cpi_imu_chain_assemble).
-    Device tensors.  Returns (D [n+1,225], E [n,225], rhs [n+1,15])."""
+    Device tensors.  Damping: lam * I, or with diagonal_damping lam * clamp(diag, 1e-6, 1e32) (GTSAM's LevenbergMarquardtParams::diagonalDamping).
+    Returns (D [n+1,225], E [n,225], rhs [n+1,15])."""
     import torch
 
     lib = capi.load()
@@ -133,7 +134,7 @@ def chain_assemble(G11, G12, G22, g1, g2, lam=0.0, prior_info0=None, prior_rhs0=
     E = torch.empty((max(n, 1), 225), dtype=torch.float64, device=dev)
     rhs = torch.empty((n + 1, 15), dtype=torch.float64, device=dev)
     st = stream if stream is not None else torch.cuda.current_stream()
-    capi.check(lib.cpi_imu_chain_assemble(n, _tptr(G11), _tptr(G12), _tptr(G22), _tptr(g1), _tptr(g2), float(lam), _tptr(prior_info0), _tptr(prior_rhs0),
+    capi.check(lib.cpi_imu_chain_assemble(n, _tptr(G11), _tptr(G12), _tptr(G22), _tptr(g1), _tptr(g2), float(lam), int(bool(diagonal_damping)), _tptr(prior_info0), _tptr(prior_rhs0),
                                           _tptr(D), _tptr(E), _tptr(rhs), ctypes.c_void_p(st.cuda_stream)))
     return D, E[:n], rhs
 
@@ -156,10 +157,11 @@ def chain_solve(D, E, rhs, stream=None, workspace=None):
 _PRIOR = {}
 
 
-def chain_lm_step(model, states, records, lin, lam=0.0, prior_sigma=1e-4, stream=None):
+def chain_lm_step(model, states, records, lin, lam=1e-5, prior_sigma=1e-4, stream=None, diagonal_damping=True):
     """One damped Gauss-Newton (Levenberg-Marquardt) step of an IMU-only chain, entirely on the device:
     evaluateError for every factor -> information blocks -> block-tridiagonal assembly (prior 1/prior_sigma^2 on x_0: the
-    reference initialises with cov = 1e-8 I, GraphSolver.cpp:331) -> block-cyclic-reduction solve -> JPLNavState::retract.
+    reference initialises with cov = 1e-8 I, GraphSolver.cpp:331; Marquardt damping lam * diag by default, lam = GTSAM's lambdaInitial:
+    an undamped IMU-only chain of thousands of keyframes is numerically singular in fp64) -> block-cyclic-reduction solve -> JPLNavState::retract.
     Returns (new_states, delta, cost = sum e^T P^-1 e before the step)."""
     import torch
 
@@ -169,7 +171,7 @@ def chain_lm_step(model, states, records, lin, lam=0.0, prior_sigma=1e-4, stream
         _PRIOR[key] = (torch.eye(15, dtype=torch.float64, device=dev) / (prior_sigma * prior_sigma)).reshape(-1).contiguous()
     e, H1, H2 = factor_eval(model, states, records, lin, stream=stream)
     G11, G12, G22, g1, g2, f = factor_hessian(model, records, e, H1, H2, stream=stream)
-    D, E, rhs = chain_assemble(G11, G12, G22, g1, g2, lam, _PRIOR[key], None, stream=stream)
+    D, E, rhs = chain_assemble(G11, G12, G22, g1, g2, lam, _PRIOR[key], None, stream=stream, diagonal_damping=diagonal_damping)
     dx = chain_solve(D, E, rhs, stream=stream)
     return retract(states, dx, stream=stream), dx, f.sum()
 

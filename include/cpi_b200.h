@@ -171,15 +171,19 @@ int cpi_imu_factor_whiten_batch(int model, int64_t n_factors, const double* reco
  * IMU-only chain x_0 - x_1 - ... - x_n (factor f links states f and f+1): what the smoother assembles and solves after the
  * linearisation (solvers/GraphSolver.cpp:202-203), on the device.
  *   cpi_imu_chain_assemble   scatter-add of the blocks of cpi_imu_factor_hessian_batch into the block-tridiagonal normal equations:
- *       D[k] (n+1 blocks 15x15) = G22[k-1] + G11[k] + lambda I (+ prior_info0 on x_0),  E[k] (n blocks, block (k,k+1)) = G12[k],
- *       rhs[k] (15) = g2[k-1] + g1[k] (+ prior_rhs0).  prior_* may be NULL; lambda = Levenberg damping.
+ *       D[k] (n+1 blocks 15x15) = G22[k-1] + G11[k] (+ prior_info0 on x_0) + damping,  E[k] (n blocks, block (k,k+1)) = G12[k],
+ *       rhs[k] (15) = g2[k-1] + g1[k] (+ prior_rhs0).  prior_* may be NULL.  Damping as in GTSAM's LevenbergMarquardtParams:
+ *       lambda I (diagonal_damping = 0, GTSAM's default) or lambda * clamp(diag D[k], 1e-6, 1e32) (diagonal_damping = 1, Marquardt).
+ *       NOTE: an IMU-only chain anchored by one prior is numerically singular in fp64 beyond a few hundred keyframes with
+ *       undamped / lambda-I normal equations (the drift modes carry ~1e-16 of the largest eigenvalue) -- for ANY elimination order;
+ *       diagonal damping (or the camera factors of the real graph) restores a well-posed system.
  *   cpi_imu_chain_solve      x = (that SPD block-tridiagonal matrix)^-1 rhs by block cyclic reduction (Cholesky on the 15x15 pivots):
  *       ~2 log2(n) + 1 kernel launches instead of an n-step sequential block recurrence.  `workspace`: device buffer of
  *       cpi_imu_chain_solve_workspace(n_states) bytes.  The step is then applied with cpi_retract_batch.
  * All pointers are DEVICE pointers.  PARITY UNPINNED; validated against banded / dense CPU solves of the same system.
  */
 int cpi_imu_chain_assemble(int64_t n_factors, const double* G11, const double* G12, const double* G22,
-                           const double* g1, const double* g2, double lambda,
+                           const double* g1, const double* g2, double lambda, int diagonal_damping,
                            const double* prior_info0, const double* prior_rhs0,
                            double* D, double* E, double* rhs, void* stream);
 int64_t cpi_imu_chain_solve_workspace(int64_t n_states);

@@ -399,12 +399,51 @@ def test_whitened_form_against_numpy(cuda, model):
     assert worst <= 1e-9
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 7, 64, 300, 4999])
-def test_chain_assemble_and_block_cyclic_reduction_solve(cuda, n):
-    """IMU-only chain of n factors: device assembly of the block-tridiagonal normal equations + block-cyclic-reduction solve, against a
-    CPU banded Cholesky (scipy.linalg.solveh_banded) of the same system.  PARITY UNPINNED (the reference hands this to GTSAM's smoother,
-    GraphSolver.cpp:202-203); odd / even / power-of-two chain lengths exercise every end case of the reduction."""
+def _chain_truth(Dh, Eh, bh):
+    """(x_true, x_banded64): scipy's banded Cholesky of the Jacobi-scaled system, then iterative refinement with 80-bit residuals --
+    the refined solution is the ground truth, the unrefined one shows what a sequential fp64 CPU elimination achieves on this system."""
     import scipy.linalg
+    n = len(Dh) - 1
+    N = 15 * (n + 1)
+    Dm = Dh.reshape(n + 1, 15, 15).transpose(0, 2, 1)               # column-major storage -> [k, row, col]
+    Em = Eh.reshape(n, 15, 15).transpose(0, 2, 1) if n else np.zeros((0, 15, 15))
+    sc = 1.0 / np.sqrt(np.einsum("kii->ki", Dm).reshape(-1))
+    ab = np.zeros((30, N))
+    for k in range(n + 1):
+        for c in range(15):
+            col = 15 * k + c
+            ab[0:15 - c, col] = Dm[k, c:, c]
+            if k < n:
+                ab[15 - c:30 - c, col] = Em[k, c, :]                 # block (k, k+1): the lower part holds E^T at rows 15(k+1).., column 15k+c
+    for col in range(N):
+        m = min(30, N - col)
+        ab[:m, col] *= sc[col] * sc[col:col + m]
+    cb = scipy.linalg.cholesky_banded(ab, lower=True)
+    solve = lambda r: scipy.linalg.cho_solve_banded((cb, True), np.asarray(r, dtype=np.float64).reshape(-1) * sc).reshape(n + 1, 15) * sc.reshape(n + 1, 15)
+    Dl, El, bl = Dm.astype(np.longdouble), Em.astype(np.longdouble), bh.astype(np.longdouble)
+
+    def residual(x):
+        r = bl - np.einsum("krc,kc->kr", Dl, x)
+        if n:
+            r[:-1] -= np.einsum("krc,kc->kr", El, x[1:])
+            r[1:] -= np.einsum("kcr,kc->kr", El, x[:-1])
+        return r
+    x64 = solve(bh)
+    x = x64.astype(np.longdouble)
+    for _ in range(6):
+        x = x + solve(residual(x).astype(np.float64)).astype(np.longdouble)
+    return x.astype(np.float64), x64
+
+
+@pytest.mark.parametrize("damping", ["lambda_I", "diagonal"])
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 64, 300, 4999])
+def test_chain_assemble_and_block_cyclic_reduction_solve(cuda, n, damping):
+    """IMU-only chain of n factors: device assembly of the block-tridiagonal normal equations + block-cyclic-reduction solve, against a
+    CPU banded Cholesky of the same system refined with 80-bit residuals.  PARITY UNPINNED (the reference hands this to GTSAM's smoother,
+    GraphSolver.cpp:202-203); odd / even / power-of-two chain lengths exercise every end case of the reduction.
+    An IMU-only chain with one prior and lambda-I damping is close to numerically singular in fp64 for any elimination order (a plain
+    banded fp64 Cholesky is ~1e-6 off at 300+ keyframes): there the gate is 'as accurate as the sequential CPU elimination', with
+    Marquardt (diagonal) damping the system is well posed and the gate is absolute."""
     from cpi_b200 import preint, factor
     torch = cuda
     model = 1
@@ -415,45 +454,25 @@ def test_chain_assemble_and_block_cyclic_reduction_solve(cuda, n):
     e, H1, H2 = factor.factor_eval(model, dX, dR, dL)
     G11, G12, G22, g1, g2, f = factor.factor_hessian(model, dR, e, H1, H2)
     prior = (torch.eye(15, dtype=torch.float64, device="cuda") * 1e8).reshape(-1).contiguous()
-    D, E, rhs = factor.chain_assemble(G11, G12, G22, g1, g2, 1e-3, prior, None)
+    lam, diag = (1e-3, False) if damping == "lambda_I" else (1e-5, True)
+    D, E, rhs = factor.chain_assemble(G11, G12, G22, g1, g2, lam, prior, None, diagonal_damping=diag)
     x = factor.chain_solve(D, E, rhs)
     torch.cuda.synchronize()
     Dh, Eh, bh, xh = D.cpu().numpy(), E.cpu().numpy(), rhs.cpu().numpy(), x.cpu().numpy()
     # assembly against numpy
     G11h, G12h, G22h, g1h, g2h = (t.cpu().numpy() for t in (G11, G12, G22, g1, g2))
-    Dref = np.zeros((n + 1, 225)); Dref[:n] += G11h; Dref[1:] += G22h; Dref[:, ::16] += 1e-3; Dref[0, ::16] += 1e8
+    Dref = np.zeros((n + 1, 225)); Dref[:n] += G11h; Dref[1:] += G22h; Dref[0, ::16] += 1e8
+    Dref[:, ::16] += lam * np.clip(Dref[:, ::16], 1e-6, 1e32) if diag else lam
     bref = np.zeros((n + 1, 15)); bref[:n] += g1h; bref[1:] += g2h
-    assert np.array_equal(Eh, G12h) and np.allclose(Dh, Dref, rtol=1e-15, atol=0) and np.allclose(bh, bref, rtol=1e-15, atol=0)
-    # banded reference solve (lower form, bandwidth 29), Jacobi-scaled like any sane CPU solve of this badly scaled system
-    N = 15 * (n + 1)
-    sc = 1.0 / np.sqrt(np.concatenate([Dh[k].reshape(15, 15, order="F").diagonal() for k in range(n + 1)]))
-    ab = np.zeros((30, N))
-    for k in range(n + 1):
-        Dk = Dh[k].reshape(15, 15, order="F")
-        for c in range(15):
-            col = 15 * k + c
-            ab[0:15 - c, col] = Dk[c:, c]
-            if k < n:
-                Ek = Eh[k].reshape(15, 15, order="F")          # block (k, k+1): rows 15k.., cols 15(k+1)..; lower part holds E^T at rows 15(k+1).., col 15k+c
-                ab[15 - c:30 - c, col] = Ek[c, :]
-    for col in range(N):
-        m = min(30, N - col)
-        ab[:m, col] *= sc[col] * sc[col:col + m]
-    xr = scipy.linalg.solveh_banded(ab, bh.reshape(-1) * sc, lower=True) * sc
-    err = np.linalg.norm(xh.reshape(-1) - xr) / np.linalg.norm(xr)
-    # residual of the device solution in the original system
-    r = np.zeros((n + 1, 15))
-    for k in range(n + 1):
-        r[k] = Dh[k].reshape(15, 15, order="F") @ xh[k] - bh[k]
-        if k < n:
-            Ek = Eh[k].reshape(15, 15, order="F")
-            r[k] += Ek @ xh[k + 1]; r[k + 1] += Ek.T @ xh[k]
-    # Jacobi-scaled normwise backward error (the raw system spans 1e8 .. 1e13: a residual relative to |b| alone is meaningless)
-    rs = r.reshape(-1) * sc
-    As = np.sqrt(sum(np.sum((Dh[k].reshape(15, 15, order="F") * sc[15 * k:15 * k + 15, None] * sc[None, 15 * k:15 * k + 15]) ** 2) for k in range(n + 1)))
-    res = np.linalg.norm(rs) / (As * np.linalg.norm(xh.reshape(-1) / sc) + np.linalg.norm(bh.reshape(-1) * sc))
-    print(n, "rel err vs banded CPU solve", err, "scaled backward error", res)
-    assert err <= 1e-7          # the backward error is printed for the record only: tiny chains are dominated by the 1e8 prior and |b| ~ 0
+    assert np.array_equal(Eh, G12h) and np.allclose(Dh, Dref, rtol=1e-14, atol=0) and np.allclose(bh, bref, rtol=1e-14, atol=1e-300)
+    assert np.all(np.isfinite(xh))
+    xt, x64 = _chain_truth(Dh, Eh, bh)
+    nt = np.linalg.norm(xt)
+    err, err64 = np.linalg.norm(xh - xt) / nt, np.linalg.norm(x64 - xt) / nt
+    print(n, damping, "device BCR rel err vs refined truth", err, "| plain fp64 banded Cholesky (CPU)", err64)
+    assert err <= 50 * max(err64, 1e-13)         # a different elimination order: same error class as the sequential fp64 solve
+    if diag:
+        assert err <= 1e-9
 
 
 def test_chain_lm_step_reduces_the_cost(cuda):
@@ -468,7 +487,7 @@ def test_chain_lm_step_reduces_the_cost(cuda):
     rng = np.random.default_rng(3)
     Xp = X.copy(); Xp[1:, 7:10] += rng.normal(0, 1e-3, (n, 3)); Xp[1:, 13:16] += rng.normal(0, 1e-3, (n, 3)); Xp[1:, 4:7] += rng.normal(0, 1e-5, (n, 3))
     dX, dR, dL = (torch.from_numpy(a).cuda() for a in (Xp, rec, L))
-    X1, dx, c0 = factor.chain_lm_step(1, dX, dR, dL)
+    X1, dx, c0 = factor.chain_lm_step(1, dX, dR, dL)                 # defaults: lambda = 1e-5 (GTSAM's lambdaInitial), diagonal damping
     X2, dx2, c1 = factor.chain_lm_step(1, X1, dR, dL)
     X3, dx3, c2 = factor.chain_lm_step(1, X2, dR, dL)
     torch.cuda.synchronize()
