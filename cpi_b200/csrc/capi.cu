@@ -1,5 +1,6 @@
 // extern "C" boundary of libcpi_b200.so (declared in include/cpi_b200.h).  Plain pointers and sizes only.
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
@@ -55,7 +56,7 @@ int device_info(DevInfo& d) {
 
 // grow-only scratch buffers for the *_host entry points (per process; guarded by one mutex: host calls serialise)
 struct Scratch {
-    static constexpr int NSTREAM = 4;
+    static constexpr int NSTREAM = 8;
     void* dev[8] = {nullptr}; size_t dev_sz[8] = {0};
     cudaStream_t stream = nullptr;            // copy-in / general stream
     cudaStream_t work[NSTREAM] = {nullptr};   // one per pipeline chunk (kernel + copy-out)
@@ -63,6 +64,7 @@ struct Scratch {
     int device = -1;
 };
 std::mutex g_scratch_mu;
+double g_host_submit_ms = 0.0, g_host_total_ms = 0.0;   // last cpi_preintegrate_batch_host call: time to enqueue everything / until drained
 Scratch g_scratch;
 
 int scratch_prepare() {
@@ -99,7 +101,8 @@ int dev_buf(int slot, size_t bytes, void** out) {
 }
 
 int preintegrate_dev(int model, int dtype, int64_t n_windows, const int64_t* sample_offsets, int64_t ns_uniform,
-                            const void* samples, const void* lin, const double* sigmas, int flags, void* out_records, void* stream, int wpb) {
+                            const void* samples, const void* lin, const double* sigmas, int flags, void* out_records, void* stream, int wpb,
+                            const void* init_records = nullptr) {
     if (model != 1 && model != 2) return fail(CPI_EINVAL, "model must be 1 or 2 (got %d)", model);
     if (dtype != 64 && dtype != 32) return fail(CPI_EINVAL, "dtype must be 64 or 32 (got %d)", dtype);
     if (n_windows < 0 || (!sample_offsets && ns_uniform < 0)) return fail(CPI_EINVAL, "negative count");
@@ -114,7 +117,9 @@ int preintegrate_dev(int model, int dtype, int64_t n_windows, const int64_t* sam
     if (rc) return rc;
     cpi::PreintParams p;
     p.n_windows = n_windows; p.offsets = sample_offsets; p.ns_uniform = ns_uniform;
-    p.samples = samples; p.lin = lin; p.out = out_records;
+    p.samples = samples; p.lin = lin; p.out = out_records; p.init = init_records;
+    if (init_records && (!cpi::preint_tri_supported(model, flags) || getenv("CPI_B200_LEGACY")))
+        return fail(CPI_EINVAL, "continuation is implemented for the default modes only (no imu_avg, model 2 with state_transition_jacobians)");
     p.q_w = sigmas[0] * sigmas[0]; p.q_wb = sigmas[1] * sigmas[1]; p.q_a = sigmas[2] * sigmas[2]; p.q_ab = sigmas[3] * sigmas[3];
     p.wpb = wpb;
     int launches = 0;
@@ -149,6 +154,11 @@ int cpi_preintegrate_batch(int model, int dtype, int64_t n_windows, const int64_
     return preintegrate_dev(model, dtype, n_windows, sample_offsets, ns_uniform, samples, lin, sigmas, flags, out_records, stream, 0);
 }
 
+int cpi_preintegrate_batch_continue(int model, int dtype, int64_t n_windows, const int64_t* sample_offsets, int64_t ns_uniform,
+                                    const void* samples, const void* lin, const double* sigmas, int flags, void* records, void* stream) {
+    return preintegrate_dev(model, dtype, n_windows, sample_offsets, ns_uniform, samples, lin, sigmas, flags, records, stream, 0, records);
+}
+
 int cpi_preintegrate_batch_host(int model, int dtype, int64_t n_windows, const int64_t* sample_offsets, int64_t ns_uniform,
                                 const void* samples, const void* lin, const double* sigmas, int flags, void* out_records) {
     if (model != 1 && model != 2) return fail(CPI_EINVAL, "model must be 1 or 2 (got %d)", model);
@@ -181,23 +191,59 @@ int cpi_preintegrate_batch_host(int model, int dtype, int64_t n_windows, const i
 
     // Chunked pipeline: H2D of chunk k+1 runs under the kernel of chunk k, D2H of chunk k under the kernel of chunk k+1.  The
     // default kernels are one-warp CTAs, so chunk kernels of different streams co-reside on the SMs and a batch can be cut into
-    // many small chunks: the tail after the last H2D is then one SMALL kernel (few warps per SM run the 200-sample chain faster
-    // than a full SM) plus a small D2H.  The lane-per-window kernels (imu_avg / analytic modes) are launched with the windows-per-
-    // block the WHOLE batch would use, so that a chunk occupies only its share of the SMs.
+    // many small chunks.  The lane-per-window kernels (imu_avg / analytic modes) are launched with the windows-per-block the WHOLE
+    // batch would use, so that a chunk occupies only its share of the SMs.
+    //
+    // Wavefront schedule (uniform layout, fp64, default modes).  A window is a chain of ns DEPENDENT samples (~3.7 us each on B200,
+    // whatever the occupancy), so a chunk that travels whole finishes ~ns x 3.7 us after it arrived, however small it is: 0.74 ms
+    // behind the last byte of H2D for 200-sample windows, a quarter of the PCIe time of the whole 10k-window batch.  Instead the batch
+    // is cut into G window groups x S sample segments, and the (group, segment) tiles are sent along ANTI-DIAGONALS: tile (g, s) is a
+    // strided copy (cudaMemcpy2DAsync: rows = windows of the group, row = samples [s ns/S, (s+1) ns/S)) followed, on the group's stream,
+    // by a CONTINUATION kernel over the group (cpi_preintegrate_batch_continue).  Every group's chain then runs WHILE its samples
+    // arrive, S other groups keep the SMs busy in between, groups finish (and copy out) one after the other, and what is left behind
+    // the last byte is one segment of one group + that group's D2H.  fp64 only: a float record would round the fp64-accumulated
+    // covariance state at every segment.
     const size_t in_bytes = (size_t)entries * CPI_SAMPLE_DOUBLES * es;
     const int cap = cpi::preint_cap(model, dtype, flags, d.sms);     // windows per CTA of the kernel preint_launch will select
     const bool small_ctas = cap <= 16;
+    const bool big = in_bytes >= ((size_t)16 << 20) && n_windows >= 8 * (int64_t)d.sms;
     int nchunk = 1;
-    if (in_bytes >= ((size_t)16 << 20) && n_windows >= 8 * (int64_t)d.sms) {
-        nchunk = small_ctas ? (int)(in_bytes >> 23) : Scratch::NSTREAM;          // ~8 MB of samples per chunk
-        if (nchunk < Scratch::NSTREAM) nchunk = Scratch::NSTREAM;
+    if (big) {
+        nchunk = small_ctas ? (int)(in_bytes >> 23) : 4;             // ~8 MB of samples per chunk
+        if (nchunk < 4) nchunk = 4;
         if (nchunk > 16) nchunk = 16;
     }
     if (const char* e = getenv("CPI_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 64) nchunk = v; }   // A/B measurements
     int64_t need = (n_windows + d.sms - 1) / d.sms;
     const int wpb = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
     const int64_t blocks = (n_windows + wpb - 1) / wpb;
-    const int64_t blocks_per_chunk = (blocks + nchunk - 1) / nchunk;
+    // wavefront geometry: the first wave_H % of the windows travel as whole-window chunks, the rest as G groups x S segments.
+    // Defaults (measured on B200, tools/host_pipeline_probe.py, profiles/r02_host_pipeline_probe.json): every copy costs ~3.5 us of dead
+    // time on the copy engine, so few large tiles beat a fine wavefront -- ONE group of 4 segments, sized so that its transfer lasts
+    // about as long as its sample chain (ns x ~4.6 us incl. the per-segment record reload, x ~50 GB/s of PCIe; model 2 chains are
+    // ~1.5x longer), behind whole-window chunks for everything before it.
+    int wave_G = 0, wave_S = 0, wave_H = 0;
+    if (big) {
+        wave_G = 1;
+        wave_S = (int)(ns_uniform / 8 < 4 ? ns_uniform / 8 : 4);
+        const double tail_bytes = (double)ns_uniform * (model == 1 ? 231e3 : 344e3);
+        const double frac = tail_bytes / (double)in_bytes;
+        wave_H = frac >= 1.0 ? 0 : (int)(100.0 * (1.0 - frac));
+        if (wave_H > 95) wave_H = 95;
+    }
+    if (const char* e = getenv("CPI_B200_HOST_WAVE")) {              // "G,S[,H]": A/B measurements and tests ("0,0" = whole-window chunks only)
+        int a_ = 0, b_ = 0, c_ = 0;
+        const int nf = sscanf(e, "%d,%d,%d", &a_, &b_, &c_);
+        if (nf >= 2 && a_ >= 0 && a_ <= 256 && b_ >= 0 && b_ <= 64 && c_ >= 0 && c_ < 100) { wave_G = a_; wave_S = b_; wave_H = nf == 3 ? c_ : 0; }
+    }
+    const bool wave = dtype == 64 && !sample_offsets && !avg && small_ctas && cpi::preint_tri_supported(model, flags) && !getenv("CPI_B200_LEGACY") &&
+                      wave_G >= 1 && wave_S >= 2 && ns_uniform >= 2 * (int64_t)wave_S;
+    const int64_t head_blocks = wave ? blocks * wave_H / 100 : blocks;
+    const int64_t head_hi = wave ? head_blocks * wpb : n_windows;    // windows [0, head_hi) travel whole, [head_hi, n) as the wavefront
+    if (wave && head_blocks > 0) { nchunk = (int)((int64_t)nchunk * wave_H / 100); if (nchunk < 1) nchunk = 1; }
+    const int64_t blocks_per_chunk = (head_blocks + nchunk - 1) / nchunk > 0 ? (head_blocks + nchunk - 1) / nchunk : 1;
+    const auto t_start = std::chrono::steady_clock::now();
+    int used = 0;                                                    // streams handed out so far (round robin)
 
     cudaStream_t s_in = g_scratch.stream;
     rc = CPI_OK;
@@ -206,8 +252,9 @@ int cpi_preintegrate_batch_host(int model, int dtype, int64_t n_windows, const i
     if (sample_offsets) CUX(cudaMemcpyAsync(d_off, sample_offsets, (size_t)(n_windows + 1) * 8, cudaMemcpyHostToDevice, s_in));
     for (int k = 0; k < nchunk; k++) {
         const int64_t lo = (int64_t)k * blocks_per_chunk * wpb;
-        if (lo >= n_windows) break;
-        const int64_t hi = (lo + blocks_per_chunk * wpb < n_windows) ? lo + blocks_per_chunk * wpb : n_windows;
+        if (lo >= head_hi) break;
+        const int64_t hi = (lo + blocks_per_chunk * wpb < head_hi) ? lo + blocks_per_chunk * wpb : head_hi;
+        used = k + 1;
         const int64_t e_lo = sample_offsets ? sample_offsets[lo] : lo * ent_w, e_hi = sample_offsets ? sample_offsets[hi] : hi * ent_w;
         const int si = k % Scratch::NSTREAM;
         cudaStream_t sk = g_scratch.work[si];
@@ -228,8 +275,40 @@ int cpi_preintegrate_batch_host(int model, int dtype, int64_t n_windows, const i
         CUX(cudaMemcpyAsync((char*)out_records + (size_t)lo * rd * es, (const char*)d_o + (size_t)lo * rd * es, (size_t)(hi - lo) * rd * es,
                             cudaMemcpyDeviceToHost, sk));
     }
+    if (wave && head_hi < n_windows) {
+        const size_t sb = (size_t)CPI_SAMPLE_DOUBLES * es;            // bytes per sample
+        const int64_t wblocks = blocks - head_blocks;
+        const int64_t bpg = (wblocks + wave_G - 1) / wave_G;          // blocks per group
+        const int64_t G = (wblocks + bpg - 1) / bpg;
+        const int64_t seg_len = (ns_uniform + wave_S - 1) / wave_S;
+        const int64_t S = (ns_uniform + seg_len - 1) / seg_len;
+        for (int64_t t = 0; t < G + S - 1; t++) {
+            for (int64_t g = t - S + 1 > 0 ? t - S + 1 : 0; g <= t && g < G; g++) {      // oldest group (latest segment) first
+                const int64_t sidx = t - g, s0 = sidx * seg_len;
+                const int64_t len = s0 + seg_len <= ns_uniform ? seg_len : ns_uniform - s0;
+                const int64_t lo = head_hi + g * bpg * wpb, hi = (lo + bpg * wpb < n_windows) ? lo + bpg * wpb : n_windows, ng = hi - lo;
+                const int si = (int)((used + g) % Scratch::NSTREAM);
+                cudaStream_t sk = g_scratch.work[si];
+                char* d_lg = (char*)d_l + (size_t)lo * CPI_LIN_DOUBLES * es;
+                char* d_og = (char*)d_o + (size_t)lo * rd * es;
+                if (sidx == 0)
+                    CUX(cudaMemcpyAsync(d_lg, (const char*)lin + (size_t)lo * CPI_LIN_DOUBLES * es, (size_t)ng * CPI_LIN_DOUBLES * es, cudaMemcpyHostToDevice, s_in));
+                // the tiles of a group are compact ([window][len]) and together fill the group's share of the device sample buffer
+                char* d_seg = (char*)d_s + ((size_t)lo * ns_uniform + (size_t)ng * s0) * sb;
+                CUX(cudaMemcpy2DAsync(d_seg, (size_t)len * sb, (const char*)samples + ((size_t)lo * ns_uniform + (size_t)s0) * sb, (size_t)ns_uniform * sb,
+                                      (size_t)len * sb, (size_t)ng, cudaMemcpyHostToDevice, s_in));
+                CUX(cudaEventRecord(g_scratch.ev[si], s_in));
+                CUX(cudaStreamWaitEvent(sk, g_scratch.ev[si], 0));
+                rc = preintegrate_dev(model, dtype, ng, nullptr, len, d_seg, d_lg, sigmas, flags, d_og, sk, wpb, sidx > 0 ? d_og : nullptr);
+                if (rc) goto drain;
+                if (sidx == S - 1)
+                    CUX(cudaMemcpyAsync((char*)out_records + (size_t)lo * rd * es, d_og, (size_t)ng * rd * es, cudaMemcpyDeviceToHost, sk));
+            }
+        }
+    }
 drain:
 #undef CUX
+    g_host_submit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
     for (int k = 0; k < Scratch::NSTREAM; k++) {
         cudaError_t e_ = cudaStreamSynchronize(g_scratch.work[k]);
         if (e_ != cudaSuccess && rc == CPI_OK) rc = fail(CPI_ECUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e_));
@@ -238,7 +317,14 @@ drain:
         cudaError_t e_ = cudaStreamSynchronize(s_in);
         if (e_ != cudaSuccess && rc == CPI_OK) rc = fail(CPI_ECUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e_));
     }
+    g_host_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
     return rc;
+}
+
+int cpi_host_last_timing(double* submit_ms, double* total_ms) {
+    if (submit_ms) *submit_ms = g_host_submit_ms;
+    if (total_ms) *total_ms = g_host_total_ms;
+    return CPI_OK;
 }
 
 int cpi_host_register(void* ptr, size_t bytes) {

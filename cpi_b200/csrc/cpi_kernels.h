@@ -12,6 +12,7 @@ struct PreintParams {
     const void* samples;      // device, double (dtype 64) or float (dtype 32)
     const void* lin;          // device
     void* out;                // device
+    const void* init;         // device, may be null: records holding the state to CONTINUE from (may alias `out`); tri-lane kernels only
     double q_w, q_wb, q_a, q_ab;   // sigma^2  (CpiBase.h:54-57)
     int wpb;                  // windows per block; 0 on entry = let preint_launch choose (one wave if possible)
 };

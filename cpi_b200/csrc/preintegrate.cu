@@ -1306,6 +1306,7 @@ cudaError_t preint_launch(int model, int dtype, int flags, const PreintParams& p
         if (launches) *launches = 1;
         return preint_launch_tri(model, dtype, p, num_sms, st);
     }
+    if (p.init) return cudaErrorNotSupported;      // continuation exists for the default (tri-lane) modes only
     // fp32 tiles are small enough that the fused kernel holds 128 windows (4 full warps) per SM: for batches beyond one wave
     // of the warp-specialised kernel it is the faster one (measured: 14.2 vs 13.1 M windows/s on 125k x 200)
     const bool ws_pays = dtype != 32 || p.n_windows <= (int64_t)num_sms * TileWS<float>::S;

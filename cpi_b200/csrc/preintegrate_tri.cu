@@ -570,6 +570,42 @@ __global__ void __launch_bounds__((TriNT<MODEL, T>::NT), 1) k_preintegrate_tri(c
     for (int e = 0; e < 33; e++) PST(e) = 0.0;
 #endif
 
+    // ---- continuation: resume from the state a previous call left in a record (the batched form of calling feed_IMU again on an existing
+    // CpiV1 / CpiV2 object, CpiBase.h:86 -- every field of the object is in the record; model 2's clone rows are re-initialised at every
+    // step, CpiV2.h:436-443, so P_meas is all of the covariance state).  The mirror image of the record write at the end of the kernel.
+    if (p.init != nullptr && active) {
+        constexpr int RDI = (MODEL == 1) ? CPI_REC_V1_DOUBLES : CPI_REC_V2_DOUBLES;
+        const T* rin = reinterpret_cast<const T*>(p.init) + win * (int64_t)RDI;
+        const int ri[3] = {i0, i1, i2};
+        DT = (double)rin[CPI_REC_DT];
+        FST(FS_AL) = (double)rin[CPI_REC_ALPHA + c]; FST(FS_BE) = (double)rin[CPI_REC_BETA + c];
+        const T* Pm = rin + CPI_REC_P;
+        pgg = (double)Pm[3 + 15 * 3]; paa = (double)Pm[9 + 15 * 9];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int r = ri[k];
+#pragma unroll
+            for (int j = 0; j < 3; j++) R[3 * k + j] = (double)rin[CPI_REC_R + r + 3 * ri[j]];     // lane frame: (row, col) = (ri[k], ri[j]) of the column-major record
+            if (MODEL == 1) {
+                FST(FS_JQ + k) = (double)rin[CPI_REC_JQ + r + 3 * c]; FST(FS_JA + k) = (double)rin[CPI_REC_JA + r + 3 * c]; FST(FS_JB + k) = (double)rin[CPI_REC_JB + r + 3 * c];
+                FST(FS_HA + k) = (double)rin[CPI_REC_HA + r + 3 * c]; FST(FS_HB + k) = (double)rin[CPI_REC_HB + r + 3 * c];
+            } else {
+                FST(FS_DTG + k) = -(double)rin[CPI_REC_JQ + r + 3 * c]; FST(FS_DPG + k) = (double)rin[CPI_REC_JA + r + 3 * c]; FST(FS_DVG + k) = (double)rin[CPI_REC_JB + r + 3 * c];
+                FST(FS_DPA + k) = (double)rin[CPI_REC_HA + r + 3 * c]; FST(FS_DVA + k) = (double)rin[CPI_REC_HB + r + 3 * c];
+                FST(FS_DPL + k) = (double)rin[CPI_REC_OA + r + 3 * c]; FST(FS_DVL + k) = (double)rin[CPI_REC_OB + r + 3 * c];
+            }
+            auto blk = [&](int I, int J) { return (double)Pm[(3 * I + r) + 15 * (3 * J + c)]; };
+            P.TT[k] = blk(0, 0); P.VV[k] = blk(2, 2);
+#ifndef CPI_TRI_UNFUSED12
+            P.PP[k] = 0.5 * blk(4, 4);                           // PP is carried as Q with PP = Q + Q^T: the symmetric half is a valid Q
+#else
+            P.PP[k] = blk(4, 4);
+#endif
+            P.TG[k] = blk(0, 1); P.GV[k] = blk(1, 2); P.TV[k] = blk(0, 2); P.AV[k] = blk(3, 2);
+            P.TP[k] = blk(0, 4); P.GP[k] = blk(1, 4); P.AP[k] = blk(3, 4); P.VP[k] = blk(2, 4);
+        }
+    }
+
 #pragma unroll 1
     for (int it0 = 0; it0 < wmax; it0 += 3) {
         // ================= pre-pass: lane c evaluates the recurrence-free scalars of sample it0 + c =================

@@ -74,9 +74,11 @@ def preintegrate_host(model, samples, lin, sigmas, flags=0, offsets=None, ns=Non
     return out
 
 
-def preintegrate(model, samples, lin, sigmas, flags=0, offsets=None, ns=None, out=None, stream=None):
+def preintegrate(model, samples, lin, sigmas, flags=0, offsets=None, ns=None, out=None, stream=None, continue_records=None):
     """DEVICE torch tensors in/out (float64 -- or float32 for the fp32-storage variant --, contiguous, all on the current
-    CUDA device); enqueues on ``stream`` (a torch.cuda.Stream; default: torch's current stream) and does not synchronise."""
+    CUDA device); enqueues on ``stream`` (a torch.cuda.Stream; default: torch's current stream) and does not synchronise.
+    ``continue_records``: records of an earlier call, updated IN PLACE with the new samples (cpi_preintegrate_batch_continue -- the batched
+    form of calling feed_IMU again on existing objects) and returned."""
     import torch
 
     lib = capi.load()
@@ -86,6 +88,10 @@ def preintegrate(model, samples, lin, sigmas, flags=0, offsets=None, ns=None, ou
         raise ValueError("samples and lin must both be float64 or both float32")
     tdt = samples.dtype
     dev = samples.device
+    if continue_records is not None:
+        if out is not None:
+            raise ValueError("give either out or continue_records")
+        out = continue_records
     for name, t in (("lin", lin), ("offsets", offsets), ("out", out)):
         if t is not None and t.device != dev:
             raise ValueError(f"{name} lives on {t.device}, samples on {dev}: all tensors of one call must be on the same CUDA device")
@@ -110,8 +116,9 @@ def preintegrate(model, samples, lin, sigmas, flags=0, offsets=None, ns=None, ou
     # the library launches on the CURRENT device: make the tensors' device current for the call and take its stream
     with torch.cuda.device(dev):
         st = stream if stream is not None else torch.cuda.current_stream(dev)
-        capi.check(lib.cpi_preintegrate_batch(model, 64 if tdt == torch.float64 else 32, n, _tptr(offsets), int(ns), _tptr(samples), _tptr(lin), _ptr(sig), int(flags),
-                                              _tptr(out), ctypes.c_void_p(st.cuda_stream)))
+        fn = lib.cpi_preintegrate_batch if continue_records is None else lib.cpi_preintegrate_batch_continue
+        capi.check(fn(model, 64 if tdt == torch.float64 else 32, n, _tptr(offsets), int(ns), _tptr(samples), _tptr(lin), _ptr(sig), int(flags),
+                      _tptr(out), ctypes.c_void_p(st.cuda_stream)))
     return out
 
 

@@ -109,8 +109,25 @@ int cpi_preintegrate_batch(int model, int dtype, int64_t n_windows,
                            const void* samples, const void* lin, const double* sigmas, int flags,
                            void* out_records, void* stream);
 
+/*
+ * Continue n_windows preintegrations with MORE samples: `records` (device) holds, per window, the record left by an earlier
+ * cpi_preintegrate_batch / _continue call and is updated in place -- the batched form of calling feed_IMU again on existing CpiV1 /
+ * CpiV2 objects (feed_IMU accumulates into the object's fields, CpiBase.h:86, 99-124; every one of them is in the record).
+ * `samples` / `sample_offsets` / `ns_uniform` describe the NEW samples only; lin, sigmas, flags must be those of the first call.
+ * fp64: agrees with the one-shot call to rounding (~1e-15 relative; P_pp is re-split symmetrically).  dtype 32 continues from the
+ * float-rounded record (the one-shot call carries the covariance state in fp64).  Default modes only (no CPI_FLAG_IMU_AVG, model 2
+ * without CPI_FLAG_ANALYTIC_JACOBIANS): CPI_EINVAL otherwise.
+ */
+int cpi_preintegrate_batch_continue(int model, int dtype, int64_t n_windows,
+                                    const int64_t* sample_offsets, int64_t ns_uniform,
+                                    const void* samples, const void* lin, const double* sigmas, int flags,
+                                    void* records, void* stream);
+
 /* Same with HOST buffers: H2D + kernel + D2H, synchronous, through device buffers owned by the library; batches above 16 MB are
- * pipelined in up to 16 chunks (copy-in of chunk k+1 under the kernel of chunk k, copy-out under the next kernel).  sample_offsets
+ * pipelined: in up to 16 whole-window chunks (copy-in of chunk k+1 under the kernel of chunk k, copy-out under the next kernel), or
+ * -- uniform layout, fp64, default modes -- as a WAVEFRONT of (window group x sample segment) tiles: strided tile copies along
+ * anti-diagonals, each followed by a continuation kernel, so that every window's sample chain runs while its samples arrive and only
+ * one segment of one group is left behind the last byte (results agree with the device entry point to rounding, ~1e-15).  sample_offsets
  * is a HOST array.  The copies are cudaMemcpyAsync straight from / to the caller's buffers: PINNED buffers (cudaHostAlloc, or
  * cpi_host_register below) overlap with the kernels; pageable buffers are legal but the CUDA driver stages them synchronously, so
  * the pipeline degrades to copy-then-compute.  Calls from several host threads serialise on the library's scratch buffers. */
@@ -118,6 +135,10 @@ int cpi_preintegrate_batch_host(int model, int dtype, int64_t n_windows,
                                 const int64_t* sample_offsets, int64_t ns_uniform,
                                 const void* samples, const void* lin, const double* sigmas, int flags,
                                 void* out_records);
+
+/* Diagnostics of the last cpi_preintegrate_batch_host call of this process: host time until everything was enqueued, and until the
+ * streams were drained (milliseconds).  Either pointer may be NULL. */
+int cpi_host_last_timing(double* submit_ms, double* total_ms);
 
 /* Pin / unpin a caller-owned host buffer for the *_host entry points (cudaHostRegister / cudaHostUnregister), for C callers that do
  * not link the CUDA runtime themselves.  Registering is expensive (~ms per 100 MB): do it once per buffer, not per call. */

@@ -337,6 +337,79 @@ def _sample_of_windows(n, cap, S, L):
     return np.unique(np.r_[0:cap, mid:mid + cap, last_full:last_full + cap, (n // cap) * cap:n, np.arange(0, n, 401), special]).astype(np.int64)
 
 
+def _close_records(a, b, tol):
+    """Every record field of a within tol (relative Frobenius, per window) of b."""
+    from parity import REC
+    for k, (lo, hi) in REC.items():
+        if hi > a.shape[1]:
+            continue
+        num = np.linalg.norm(a[:, lo:hi] - b[:, lo:hi], axis=1); den = np.maximum(np.linalg.norm(b[:, lo:hi], axis=1), 1e-300)
+        assert np.max(num / den) <= tol, (k, float(np.max(num / den)))
+
+
+@pytest.mark.parametrize("model", [1, 2])
+def test_continuation_matches_one_shot(cuda, oracle, model):
+    """cpi_preintegrate_batch_continue: feeding a window's samples in several calls (the batched form of further feed_IMU calls on an
+    existing object, CpiBase.h:86) gives the one-shot result to rounding; a continuation with no new samples leaves the record alone."""
+    from cpi_b200 import preint
+    torch = cuda
+    n, ns = 1203, 61
+    S, L = synth.make_windows(n, ns, rate=200.0, first_window=31000)
+    dS, dL = torch.from_numpy(S).cuda(), torch.from_numpy(L).cuda()
+    one = preint.preintegrate(model, dS, dL, synth.SIGMAS, 0, ns=ns)
+    cuts = [0, 20, 21, 21, 47, ns]                                    # uniform segments of 20, 1, 0, 26 and 14 samples
+    rec = None
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        seg = dS[:, a:b, :].contiguous()
+        if rec is None:
+            rec = preint.preintegrate(model, seg, dL, synth.SIGMAS, 0, ns=b - a)
+        else:
+            before = rec.clone()
+            rec = preint.preintegrate(model, seg, dL, synth.SIGMAS, 0, ns=b - a, continue_records=rec)
+            if b == a:
+                torch.cuda.synchronize()
+                assert torch.equal(rec, before)
+    torch.cuda.synchronize()
+    _close_records(rec.cpu().numpy(), one.cpu().numpy(), 1e-12)
+    # ragged continuation (CSR offsets; some windows receive nothing) against the oracle fed all samples at once
+    rng = np.random.default_rng(5)
+    first = rng.integers(0, ns + 1, size=n); first[:4] = [0, ns, 1, ns - 1]
+    offA = np.zeros(n + 1, dtype=np.int64); offA[1:] = np.cumsum(first)
+    offB = np.zeros(n + 1, dtype=np.int64); offB[1:] = np.cumsum(ns - first)
+    SA = np.concatenate([S[i, :first[i]] for i in range(n)]); SB = np.concatenate([S[i, first[i]:] for i in range(n)])
+    rec = preint.preintegrate(model, torch.from_numpy(SA).cuda(), dL, synth.SIGMAS, 0, offsets=torch.from_numpy(offA).cuda())
+    rec = preint.preintegrate(model, torch.from_numpy(SB).cuda(), dL, synth.SIGMAS, 0, offsets=torch.from_numpy(offB).cuda(), continue_records=rec)
+    torch.cuda.synchronize()
+    got = rec.cpu().numpy()
+    _close_records(got, one.cpu().numpy(), 1e-12)
+    sel = np.r_[0:40, n - 40:n]
+    ref = oracle.preintegrate(model, S[sel], L[sel], synth.SIGMAS, 0, ns=ns, nthreads=8)
+    compare_records(got[sel], ref, model, in_band=window_band(S[sel].reshape(-1, 7), np.arange(len(sel) + 1, dtype=np.int64) * ns, L[sel]))
+    # modes without a continuation kernel refuse
+    from cpi_b200 import capi
+    with pytest.raises(capi.CpiError):
+        preint.preintegrate(model, dS, dL, synth.SIGMAS, preint.FLAG_IMU_AVG, ns=ns - 1, continue_records=one.clone())
+
+
+@pytest.mark.parametrize("model", [1, 2])
+def test_host_entry_wavefront_schedule(cuda, model, monkeypatch):
+    """The host entry point's wavefront schedule (window groups x sample segments, strided tile copies + continuation kernels), with
+    several geometries forced onto a small batch: every window within rounding of the device one-shot call."""
+    from cpi_b200 import preint
+    torch = cuda
+    n, ns = 3001, 100
+    S, L = synth.make_windows(n, ns, rate=200.0, first_window=77000)
+    one = preint.preintegrate(model, torch.from_numpy(S).cuda(), torch.from_numpy(L).cuda(), synth.SIGMAS, 0, ns=ns).cpu().numpy()
+    for spec in (None, "3,4", "1,7", "40,2", "5,64", "0,0"):       # 64 segments > ns / 2 and "0,0": whole-window chunks, bit-identical
+        if spec is None:
+            monkeypatch.delenv("CPI_B200_HOST_WAVE", raising=False)
+        else:
+            monkeypatch.setenv("CPI_B200_HOST_WAVE", spec)
+        host = preint.preintegrate_host(model, S, L, synth.SIGMAS, 0, ns=ns)
+        _close_records(host, one, 1e-12)
+        assert np.array_equal(host, one) == (spec in ("5,64", "0,0")), spec
+
+
 @pytest.mark.parametrize("model,dtype,n,ns", [(1, np.float64, 25003, 200), (1, np.float32, 25003, 200), (2, np.float64, 12037, 400), (2, np.float32, 12037, 400)])
 def test_multiwave_capacity_path(cuda, oracle, model, dtype, n, ns):
     """Batches of several waves of full-capacity CTAs (25k x 200 model 1 = 313 CTAs of 80 windows; 12k x 400 model 2): the
@@ -365,9 +438,13 @@ def test_multiwave_capacity_path(cuda, oracle, model, dtype, n, ns):
         for k, gate in FP32_GATES[model].items():
             assert worst[k] <= gate, (k, worst[k], gate)
     print(model, dtype.__name__, n, ns, len(sel), {k: f"{v:.1e}" for k, v in worst.items()})
-    # host entry point (chunk-pipelined) gives the same bits
+    # host entry point: whole-window chunks give the same bits (fp32); the fp64 wavefront schedule feeds every window in segments through
+    # continuation kernels (rounding-level differences: the symmetric blocks are re-symmetrised at every segment)
     host = preint.preintegrate_host(model, Sx, Lx, synth.SIGMAS, 0, ns=ns)
-    assert np.array_equal(host, got)
+    if dtype == np.float32:
+        assert np.array_equal(host, got)
+    else:
+        _close_records(host, got, 1e-12)
 
 
 @pytest.mark.parametrize("model", [1, 2])
