@@ -60,7 +60,12 @@ FFMA_PEAK_TFLOPS = 72.51   # same microbenchmark, fp32 FFMA
 DFMA_PEAK_TFLOPS = 34.17   # measured on this pool's B200 by tools/microbench.cu (profiles/microbench_r01.jsonl), burst == sustained
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the CURRENT kernels
 # (profiles/r02_*.txt); None where no capture exists
-NCU_TRAFFIC = {"v1_10k_200": (114.05e6 + 4.16e6, "profiles/r02_k1_tri_v1_prepass.txt")}
+NCU_TRAFFIC = {   # dram__bytes_read.sum + dram__bytes_write.sum per launch of the committed `ncu --set full` captures (algorithmic bytes in brackets)
+    "v1_10k_200": (113.96e6 + 4.29e6, "profiles/r02_k1_tri_10k_final.txt"),                # [136.2 MB incl. 23.2 MB of records; the record writes mostly stay in L2]
+    "v2_100k_400": (2.2553e9 + 246.57e6, "profiles/r02_k2_tri_100k_final.txt"),            # [2.497 GB]
+    "v1_125k_200": (1.4247e9 + 273.82e6, "profiles/r02_k1_tri_125k.txt"),                  # [1.703 GB]
+    "v1_1m_200_fp32": (709.55e6 + 129.51e6, "profiles/r02_k1_tri_fp32_125k.txt"),          # [851.5 MB]
+}
 
 
 def measured_peaks():
@@ -258,7 +263,8 @@ def run_factor(args, wl, emit=True, cpu=True):
     out = {"metric": "imu_factors_per_sec", "value": n / (ms * 1e-3), "unit": "factors/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": config_dict(wl, 1), "gpu_launches": int(launches), "kernel_ms": ms,
-           "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                        "traffic": (872.34e6 + 3662.35e6) if big else None, "traffic_source": "profiles/r02_k3_factor_1m.txt (4.496 GB algorithmic)" if big else None,
                         "note": "4 496 algorithmic B/factor; at 5k factors (22 MB) the launch is latency-sized: 22 MB at peak would take 3.4 us; the 1M-factor workload shows the bandwidth regime"},
            "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "factors/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int((hX.numel() + hR.numel() + hL.numel()) * 8),
                    "d2h_bytes_per_step": int((hE.numel() + hH1.numel() + hH2.numel()) * 8), "api": "cpi_imu_factor_eval_batch_host"}}
@@ -307,7 +313,10 @@ class Ctx:
             torch.cuda.set_device(0)
         capi.load()
         self.dev = torch.device("cuda", torch.cuda.current_device())
+        # pinned host buffers belong on the GPU's NUMA node (a remote node costs ~25 % of the H2D rate on these boxes).  N > 1: the rank binds
+        # itself for good; N = 1: only while it allocates them (measure_preint), so that the CPU-baseline leg keeps every usable core
         self.numa = None
+        self.affinity0 = os.sched_getaffinity(0)
         if self.world > 1:
             self.numa = self.pin_to_gpu_numa_node(torch)
         self.comm = None
@@ -317,8 +326,9 @@ class Ctx:
 
 
 def _pin_to_gpu_numa_node(self, torch):
-    """N > 1: bind this rank (and therefore its pinned host buffers, first-touch) to the CPUs of its GPU's NUMA node, so that eight
-    ranks do not push their H2D traffic through one socket.  Best effort: silently skipped when sysfs does not say."""
+    """Bind this process (and therefore the pinned host buffers it allocates next, first-touch) to the CPUs of its GPU's NUMA node, so that
+    H2D does not cross the socket interconnect and eight ranks do not push their traffic through one socket.  Best effort: silently
+    skipped when sysfs does not say."""
     try:
         pr = torch.cuda.get_device_properties(self.dev)
         bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
@@ -462,8 +472,13 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
         hS = torch.from_numpy(S).to(tdt); hL = torch.from_numpy(L).to(tdt)
         if reps > 1:
             hS = hS.repeat(reps, 1, 1)[:n].contiguous(); hL = hL.repeat(reps, 1)[:n].contiguous()
+        if world == 1:
+            ctx.numa = ctx.pin_to_gpu_numa_node(torch)
         hS = hS.pin_memory(); hL = hL.pin_memory()
         hO = torch.empty((n, rd), dtype=tdt).pin_memory()
+        hO.zero_()
+        if world == 1:
+            os.sched_setaffinity(0, ctx.affinity0)
         del S, L
         sig = np.ascontiguousarray(synth.SIGMAS)
         lib = capi.load()
@@ -508,7 +523,7 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
                       "pcie_floor": {"h2d_ms": h2d_ms, "h2d_gbs": hS.numel() * es / h2d_ms * 1e-6, "d2h_ms": d2h_ms,
                                      "note": "plain pinned cudaMemcpyAsync of the same bytes on this box, measured in this run; the copies run full duplex, so H2D alone is the floor of the host path"}}
         if ctx.numa:
-            out["e2e"]["host_numa"] = f"every rank bound to the NUMA node of its GPU (rank 0: node {ctx.numa['node']}, {ctx.numa['cpus']} cpus) before allocating its pinned buffers"
+            out["e2e"]["host_numa"] = f"pinned host buffers allocated on the NUMA node of the rank's GPU (rank 0: node {ctx.numa['node']}, {ctx.numa['cpus']} cpus)"
         del hS, hL, hO
     del batches, gathers
     torch.cuda.empty_cache()
