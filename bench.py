@@ -256,9 +256,10 @@ def run_factor(args, wl, emit=True, cpu=True):
     for _ in range(1 if big else 3):
         host_step()
     ke = 2 if big else 10
+    per_call = []
     t0 = time.perf_counter()
     for _ in range(ke):
-        host_step()
+        t1 = time.perf_counter(); host_step(); per_call.append((time.perf_counter() - t1) * 1e3)
     e2e_ms = (time.perf_counter() - t0) * 1e3 / ke
     out = {"metric": "imu_factors_per_sec", "value": n / (ms * 1e-3), "unit": "factors/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -267,7 +268,8 @@ def run_factor(args, wl, emit=True, cpu=True):
                         "traffic": (872.34e6 + 3662.35e6) if big else None, "traffic_source": "profiles/r02_k3_factor_1m.txt (4.496 GB algorithmic)" if big else None,
                         "note": "4 496 algorithmic B/factor; at 5k factors (22 MB) the launch is latency-sized: 22 MB at peak would take 3.4 us; the 1M-factor workload shows the bandwidth regime"},
            "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "factors/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int((hX.numel() + hR.numel() + hL.numel()) * 8),
-                   "d2h_bytes_per_step": int((hE.numel() + hH1.numel() + hH2.numel()) * 8), "api": "cpi_imu_factor_eval_batch_host"}}
+                   "d2h_bytes_per_step": int((hE.numel() + hH1.numel() + hH2.numel()) * 8), "api": "cpi_imu_factor_eval_batch_host",
+                   "ms_per_call": [round(t, 3) for t in per_call]}}
     # one Levenberg-Marquardt step of the IMU-only chain entirely on device: eval -> information blocks -> block-tridiagonal
     # assembly -> block-cyclic-reduction Cholesky solve -> retract (parity unpinned: GTSAM is not in the tree)
     if hasattr(factor, "chain_lm_step") and not big:
