@@ -383,6 +383,12 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
     # rank r's kernel writes gathers[k][r] in place; two buffers so that step i's all-gather overlaps step i+1's kernel
     gathers = [torch.empty((world, n, rd), dtype=tdt, device=dev) for _ in range(2 if world > 1 else 1)]
     stream = torch.cuda.current_stream()
+    exchange = None
+    if world > 1:
+        torch.cuda.synchronize()             # nothing of torch's own NCCL group in flight while the product communicator runs collectives
+        pushed = [ctx.comm.register(g) for g in gathers]
+        exchange = ("copy-engine peer copies of every rank's slice into CUDA-IPC mappings of the peers' gather buffers + two 1-element NCCL all-reduces as barriers"
+                    if all(pushed) else "ncclAllGather (buffers could not be exported with CUDA IPC)")
 
     def step(i):
         dS, dL = batches[i % NB]
@@ -456,7 +462,7 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
     out = {"metric": "imu_windows_per_sec", "value": value, "unit": "windows/s", "n_gpus": world, "steps": steps, "warmup": warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32 storage + f32 covariance RK4, f64 rotations/coefficients/means" if f32 else "f64", "data": "synthetic",
-           "config": cfg, "gpu_launches": int(launches), "kernel_ms": kern_ms,
+           "config": cfg, "gpu_launches": int(launches), "kernel_ms": kern_ms, **({"exchange": exchange} if exchange else {}),
            "roofline": {"bound": "fp32+fp64 CUDA cores" if f32 else "fp64", "achieved": ach_tf, "peak": FFMA_PEAK_TFLOPS if f32 else DFMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                         "frac": ach_tf / (FFMA_PEAK_TFLOPS if f32 else DFMA_PEAK_TFLOPS),
                         "traffic": NCU_TRAFFIC.get(name, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(name, (None, None))[1],

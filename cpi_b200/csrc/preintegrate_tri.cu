@@ -55,7 +55,7 @@ template <class T> CPI_DEV void gather_cols(const T* V, int nx, int pv, T* X1, T
 // slots, [entry][thread]: TV, GV, AV, VV (model 2: + CV) for the four stages.
 template <int MODEL> struct TriL {
 #ifndef CPI_TRI_UNFUSED12
-    static constexpr int NSL = (MODEL == 1 ? 6 : 9) * 4;        // TV, GV (+ CV) for the four stages
+    static constexpr int NSL = (MODEL == 1 ? 6 : 9) * 4 + (MODEL == 1 ? 0 : 9);   // TV, GV (+ CV) for the four stages; model 2: + TG(start) columns 1, 2 and TT(start) 11, 21, 22
 #else
     static constexpr int NSL = (MODEL == 1 ? 12 : 15) * 4;      // + AV, VV in the split cascade
 #endif
@@ -122,7 +122,13 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah
 #ifndef CPI_TRI_UNFUSED12
     constexpr int NS = (MODEL == 1) ? 6 : 9;              // slot entries per stage: TV, GV (+ CV)
     constexpr int SL_CV = 6;
+#ifdef CPI_TRI_M2_NOPARK
+    constexpr bool PARK = false;
 #else
+    constexpr bool PARK = MODEL == 2 && sizeof(T) == 8;   // model 2 fp64: halves the register spills (ptxas: 200 -> 116 B of spill stores per sample)
+#endif
+#else
+    constexpr bool PARK = false;
     constexpr int NS = (MODEL == 1) ? 12 : 15;            // slot entries per stage: TV, GV, AV, VV (+ CV)
     constexpr int SL_CV = 12;
 #endif
@@ -167,8 +173,19 @@ CPI_DEV void tri_cov_step(TriP<T>& P, T* sl, double* ps, const T* w, const T* ah
 #pragma unroll
                     for (int e = 0; e < 3; e++) { G1s[e] = TG1[e]; G2s[e] = TG2[e]; }
                     tts[0] = t11; tts[1] = t21; tts[2] = t22;
+                    if (PARK) {                               // constant over the step: parked in lane-private slots rather than held in 18 registers
+#pragma unroll
+                        for (int e = 0; e < 3; e++) { SLT(4 * NS + e) = TG1[e]; SLT(4 * NS + 3 + e) = TG2[e]; }
+                        SLT(4 * NS + 6) = t11; SLT(4 * NS + 7) = t21; SLT(4 * NS + 8) = t22;
+                    }
                     TC1[0] = xTT[1]; TC1[1] = t11; TC1[2] = t21; TC2[0] = xTT[2]; TC2[1] = t21; TC2[2] = t22;   // TC(start) = TT(start), symmetric
-                } else gather_cols(xTC, nx, pv, TC1, TC2);
+                } else {
+                    gather_cols(xTC, nx, pv, TC1, TC2);
+                    if (PARK) {
+#pragma unroll
+                        for (int e = 0; e < 3; e++) { G1s[e] = SLT(4 * NS + e); G2s[e] = SLT(4 * NS + 3 + e); tts[e] = SLT(4 * NS + 6 + e); }
+                    }
+                }
             }
             // TG:  -W x - pgg_s I
             cross(xTG, w, kTG);

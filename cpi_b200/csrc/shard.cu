@@ -1,19 +1,31 @@
 // Multi-GPU entry points of libcpi_b200.so (declared in include/cpi_b200.h): one process per GPU, window batches sharded
-// contiguously over the ranks, ONE in-place NCCL all-gather of the fixed-size result records per batch (the
+// contiguously over the ranks, ONE in-place all-gather of the fixed-size result records per batch (the
 // reference builds one preintegrator per factor on one CPU thread, solvers/GraphSolver_IMU.cpp:43 -- windows share nothing).
 //
-// The preintegration kernel writes this rank's records straight into its slice of the caller's gather buffer; the
-// all-gather runs on the communicator's OWN stream behind an event, so that the next batch's kernel (into a second gather
-// buffer) overlaps it: the collective is ~0.3 ms for 8 x 10k fp64 records at NVLink rate and disappears behind a 0.9 ms kernel.
+// The preintegration kernel writes this rank's records straight into its slice of the caller's gather buffer; the exchange runs
+// on the communicator's OWN stream behind an event, so that the next batch's kernel (into a second gather buffer) overlaps it.
 //
-// NCCL is bound at run time (dlopen "libnccl.so.2": the copy torch already mapped when called from Python, the system one
-// otherwise), so single-GPU users of the library need no NCCL at all.
+// Two exchange paths:
+//   PUSH (gather buffers registered with cpi_comm_register): every rank copies its slice into the peers' gather buffers over
+//        NVLink with the COPY ENGINES (cudaMemcpyAsync into CUDA-IPC mappings of the peers' buffers), bracketed by two one-element
+//        NCCL all-reduces that act as barriers ("every rank has released this buffer" before, "every slice has landed" after).
+//        No SM is involved in moving the records.  This matters because the preintegration kernel of configs[1] is a ONE-WAVE
+//        kernel (1 000 one-warp CTAs on 1 184 slots): an NCCL all-gather kernel running beside it takes whole SMs (one NCCL CTA
+//        ~ 7 of an SM's 8 slots), pushes part of the grid into a second wave and costs more than it hides (measured at N = 4:
+//        0.75 -> 0.89 ms per step).
+//   NCCL (unregistered buffers, or CUDA IPC unavailable for them): ncclAllGather on the communicator's stream, with the
+//        communicator limited to CPI_B200_NCCL_MAX_CTAS (default 16) CTAs so that the kernel beside it still fits one wave.
+//
+// NCCL and the CUDA driver are bound at run time (dlopen "libnccl.so.2" / "libcuda.so.1": the copies torch already mapped when
+// called from Python), so single-GPU users of the library need neither at link time.
 #include <dlfcn.h>
 #include <nccl.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "cpi_common.cuh"
 #include "cpi_kernels.h"
@@ -30,13 +42,18 @@ struct NcclApi {
     void* h = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;      // optional
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     ncclResult_t (*GetVersion)(int*) = nullptr;
 };
 NcclApi g_nccl;
 std::mutex g_nccl_mu;
+// cuMemGetAddressRange_v2(CUdeviceptr* base, size_t* size, CUdeviceptr ptr): the allocation a pointer lives in (for the IPC handle)
+typedef int (*cuMemGetAddressRange_t)(unsigned long long*, size_t*, unsigned long long);
+cuMemGetAddressRange_t g_addr_range = nullptr;
 
 int nccl_load() {
     std::lock_guard<std::mutex> lk(g_nccl_mu);
@@ -48,13 +65,30 @@ int nccl_load() {
     a.h = h;
 #define SYM(field, name) *(void**)(&a.field) = dlsym(h, name); if (!a.field) return cpi::capi_fail(CPI_ENODEVICE, "NCCL symbol %s missing", name)
     SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
-    SYM(AllGather, "ncclAllGather"); SYM(GetErrorString, "ncclGetErrorString"); SYM(GetVersion, "ncclGetVersion");
+    SYM(AllGather, "ncclAllGather"); SYM(AllReduce, "ncclAllReduce"); SYM(GetErrorString, "ncclGetErrorString"); SYM(GetVersion, "ncclGetVersion");
 #undef SYM
+    *(void**)(&a.CommInitRankConfig) = dlsym(h, "ncclCommInitRankConfig");
+    if (void* cu = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL)) {
+        *(void**)(&g_addr_range) = dlsym(cu, "cuMemGetAddressRange_v2");
+        if (!g_addr_range) *(void**)(&g_addr_range) = dlsym(cu, "cuMemGetAddressRange");
+    }
     g_nccl = a;
     return CPI_OK;
 }
 #define NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return cpi::capi_fail(CPI_ECUDA, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); } while (0)
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cpi::capi_fail(CPI_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+constexpr int MAX_WORLD = 64;
+struct IpcMsg {                       // what every rank tells the others about a gather buffer it registers
+    cudaIpcMemHandle_t handle;        // of the allocation the buffer lives in
+    uint64_t offset;                  // of the buffer inside that allocation
+    uint64_t bytes;
+    int32_t ok;                       // 0: this rank could not export the buffer -> everybody uses the NCCL path for it
+    int32_t pad;
+};
+static_assert(sizeof(IpcMsg) == 88, "IpcMsg layout");
+struct OpenedAlloc { int peer; cudaIpcMemHandle_t handle; void* base; };
+struct Registered { void* local = nullptr; size_t bytes = 0; bool push = false; char* peer[MAX_WORLD] = {nullptr}; };
 
 }  // namespace
 
@@ -62,11 +96,15 @@ struct cpi_comm {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1, device = 0;
     cudaStream_t stream = nullptr;            // communication stream
+    cudaEvent_t entry = nullptr;              // recorded on the caller's stream when the call is entered
     cudaEvent_t kernel_done = nullptr;        // recorded on the caller's stream after the kernel
     static constexpr int NBUF = 4;
     void* buf[NBUF] = {nullptr};              // gather buffers seen recently ...
-    cudaEvent_t gathered[NBUF] = {nullptr};   // ... and the event recorded behind their last all-gather
+    cudaEvent_t gathered[NBUF] = {nullptr};   // ... and the event recorded behind their last exchange
     int last = -1;
+    int* d_bar = nullptr;                     // two ints: source / sink of the barrier all-reduces
+    std::vector<Registered> regs;             // cpi_comm_register
+    std::vector<OpenedAlloc> opened;          // peer allocations mapped with cudaIpcOpenMemHandle (one mapping per allocation)
 };
 
 extern "C" {
@@ -84,7 +122,7 @@ int cpi_comm_unique_id(void* id_out) {
 
 int cpi_comm_create(const void* id_in, int rank, int world, cpi_comm** out) {
     if (!id_in || !out) return cpi::capi_fail(CPI_EINVAL, "null pointer argument");
-    if (world < 1 || rank < 0 || rank >= world) return cpi::capi_fail(CPI_EINVAL, "bad rank %d / world %d", rank, world);
+    if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world) return cpi::capi_fail(CPI_EINVAL, "bad rank %d / world %d", rank, world);
     int rc = nccl_load();
     if (rc) return rc;
     cpi_comm* c = new cpi_comm;
@@ -92,14 +130,25 @@ int cpi_comm_create(const void* id_in, int rank, int world, cpi_comm** out) {
     CU(cudaGetDevice(&c->device));
     ncclUniqueId id;
     memcpy(&id, id_in, sizeof id);
-    NC(g_nccl.CommInitRank(&c->comm, world, id, rank));
-    // highest priority: when batch i's all-gather and batch i+1's kernel become runnable together, the collective's few CTAs must get
-    // their SM slots first -- the preintegration kernel fills every SM in one wave and would otherwise starve it until it ends
+    // cap the CTAs NCCL may use: its all-gather runs BESIDE a one-wave kernel (see the header of this file)
+    int max_ctas = 16;
+    if (const char* e = getenv("CPI_B200_NCCL_MAX_CTAS")) { const int v = atoi(e); if (v >= 0 && v <= 64) max_ctas = v; }
+    if (g_nccl.CommInitRankConfig && max_ctas > 0) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.minCTAs = 1; cfg.maxCTAs = max_ctas;
+        NC(g_nccl.CommInitRankConfig(&c->comm, world, id, rank, &cfg));
+    } else {
+        NC(g_nccl.CommInitRank(&c->comm, world, id, rank));
+    }
+    // highest priority: when batch i's exchange and batch i+1's kernel become runnable together, the exchange goes first
     int prio_least = 0, prio_greatest = 0;
     CU(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
     CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
+    CU(cudaEventCreateWithFlags(&c->entry, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->kernel_done, cudaEventDisableTiming));
     for (int i = 0; i < cpi_comm::NBUF; i++) CU(cudaEventCreateWithFlags(&c->gathered[i], cudaEventDisableTiming));
+    CU(cudaMalloc(&c->d_bar, 2 * sizeof(int)));
+    CU(cudaMemset(c->d_bar, 0, 2 * sizeof(int)));
     *out = c;
     return CPI_OK;
 }
@@ -107,16 +156,82 @@ int cpi_comm_create(const void* id_in, int rank, int world, cpi_comm** out) {
 int cpi_comm_destroy(cpi_comm* c) {
     if (!c) return CPI_OK;
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& o : c->opened) cudaIpcCloseMemHandle(o.base);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->entry) cudaEventDestroy(c->entry);
     if (c->kernel_done) cudaEventDestroy(c->kernel_done);
     for (int i = 0; i < cpi_comm::NBUF; i++) if (c->gathered[i]) cudaEventDestroy(c->gathered[i]);
+    if (c->d_bar) cudaFree(c->d_bar);
     delete c;
     return CPI_OK;
 }
 
 int cpi_comm_rank(const cpi_comm* c) { return c ? c->rank : CPI_EINVAL; }
 int cpi_comm_world(const cpi_comm* c) { return c ? c->world : CPI_EINVAL; }
+
+int cpi_comm_register(cpi_comm* c, void* gather_records, size_t bytes, int* peer_copies) {
+    if (peer_copies) *peer_copies = 0;
+    if (!c || !gather_records || bytes == 0) return cpi::capi_fail(CPI_EINVAL, "null pointer argument");
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev != c->device) return cpi::capi_fail(CPI_EINVAL, "communicator was created on device %d, current device is %d", c->device, dev);
+    for (auto& r : c->regs) if (r.local == gather_records && r.bytes == bytes) { if (peer_copies) *peer_copies = r.push; return CPI_OK; }      // already registered
+    Registered reg;
+    reg.local = gather_records; reg.bytes = bytes;
+    if (c->world == 1) { c->regs.push_back(reg); return CPI_OK; }
+    // 1. export: IPC handle of the allocation + offset of the buffer inside it
+    IpcMsg mine;
+    memset(&mine, 0, sizeof mine);
+    mine.bytes = bytes;
+    static const bool no_push = getenv("CPI_B200_GATHER") && !strcmp(getenv("CPI_B200_GATHER"), "nccl");
+    if (g_addr_range && !no_push) {
+        unsigned long long base = 0; size_t asz = 0;
+        if (g_addr_range(&base, &asz, (unsigned long long)(uintptr_t)gather_records) == 0 && base != 0 &&
+            (unsigned long long)(uintptr_t)gather_records + bytes <= base + asz &&
+            cudaIpcGetMemHandle(&mine.handle, (void*)(uintptr_t)base) == cudaSuccess) {
+            mine.offset = (uint64_t)((unsigned long long)(uintptr_t)gather_records - base);
+            mine.ok = 1;
+        }
+        cudaGetLastError();                                           // an export failure is not an error of this call: the buffer takes the NCCL path
+    }
+    // 2. exchange (collective): every rank learns every handle, and whether EVERY rank could export
+    std::vector<IpcMsg> all(c->world);
+    void* d_x = nullptr;
+    CU(cudaMalloc(&d_x, sizeof(IpcMsg) * c->world));
+    CU(cudaMemcpyAsync((char*)d_x + sizeof(IpcMsg) * c->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllGather((char*)d_x + sizeof(IpcMsg) * c->rank, d_x, sizeof(IpcMsg), ncclChar, c->comm, c->stream));
+    CU(cudaMemcpyAsync(all.data(), d_x, sizeof(IpcMsg) * c->world, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(d_x));
+    bool ok = true;
+    for (int p = 0; p < c->world; p++) ok = ok && all[p].ok == 1 && all[p].bytes == bytes;
+    // 3. import the peers' allocations (one mapping per allocation and process)
+    int imported = ok ? 1 : 0;
+    if (ok) {
+        for (int p = 0; p < c->world && imported; p++) {
+            if (p == c->rank) { reg.peer[p] = (char*)gather_records; continue; }
+            void* base = nullptr;
+            for (auto& o : c->opened) if (o.peer == p && !memcmp(&o.handle, &all[p].handle, sizeof(cudaIpcMemHandle_t))) base = o.base;
+            if (!base) {
+                if (cudaIpcOpenMemHandle(&base, all[p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); imported = 0; break; }
+                c->opened.push_back(OpenedAlloc{p, all[p].handle, base});
+            }
+            reg.peer[p] = (char*)base + all[p].offset;
+        }
+    }
+    // 4. agree (collective): the push path is used only if EVERY rank imported every peer -- the choice of path must never differ between ranks
+    int agreed = 0;
+    CU(cudaMemcpyAsync(c->d_bar, &imported, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllReduce(c->d_bar, c->d_bar + 1, 1, ncclInt, ncclMin, c->comm, c->stream));
+    CU(cudaMemcpyAsync(&agreed, c->d_bar + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemsetAsync(c->d_bar, 0, 2 * sizeof(int), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    reg.push = agreed == 1;
+    c->regs.push_back(reg);
+    if (peer_copies) *peer_copies = reg.push ? 1 : 0;
+    return CPI_OK;
+}
 
 int cpi_preintegrate_batch_sharded(cpi_comm* c, int model, int dtype, int64_t n_local, const int64_t* sample_offsets, int64_t ns_uniform,
                                    const void* samples, const void* lin, const double* sigmas, int flags, void* gather_records, void* stream) {
@@ -130,19 +245,37 @@ int cpi_preintegrate_batch_sharded(cpi_comm* c, int model, int dtype, int64_t n_
     if (dev != c->device) return cpi::capi_fail(CPI_EINVAL, "communicator was created on device %d, current device is %d", c->device, dev);
     const size_t slice = (size_t)n_local * rd * (dtype == 32 ? 4 : 8);
     cudaStream_t st = (cudaStream_t)stream;
-    // this gather buffer may still be the source / destination of an earlier all-gather: order the kernel behind it
+    const Registered* reg = nullptr;
+    for (auto& r : c->regs) if (r.local == gather_records && r.push && slice * c->world <= r.bytes) reg = &r;
+    // this gather buffer may still be the source / destination of an earlier exchange: order the kernel behind it
     int slot = -1;
     for (int i = 0; i < cpi_comm::NBUF; i++) if (c->buf[i] == gather_records) slot = i;
     if (slot >= 0) CU(cudaStreamWaitEvent(st, c->gathered[slot], 0));
     else { slot = (c->last + 1) % cpi_comm::NBUF; c->buf[slot] = gather_records; }
+    if (reg && c->world > 1 && slice > 0) {
+        // barrier 1, under the kernel: the peers may write into this buffer once EVERY rank's stream has reached this call
+        // (whatever the caller enqueued before it -- e.g. the consumer of the buffer's previous contents -- is then done)
+        CU(cudaEventRecord(c->entry, st));
+        CU(cudaStreamWaitEvent(c->stream, c->entry, 0));
+        NC(g_nccl.AllReduce(c->d_bar, c->d_bar + 1, 1, ncclInt, ncclMax, c->comm, c->stream));
+    }
     int rc = cpi_preintegrate_batch(model, dtype, n_local, sample_offsets, ns_uniform, samples, lin, sigmas, flags,
                                     (char*)gather_records + (size_t)c->rank * slice, stream);
     if (rc) return rc;
     if (c->world > 1) {
         CU(cudaEventRecord(c->kernel_done, st));
         CU(cudaStreamWaitEvent(c->stream, c->kernel_done, 0));
-        if (slice > 0)
+        if (slice > 0 && reg) {
+            const char* src = (const char*)gather_records + (size_t)c->rank * slice;
+            for (int k = 1; k < c->world; k++) {                     // start with the next rank: at any moment every rank targets a different peer
+                const int p = (c->rank + k) % c->world;
+                CU(cudaMemcpyAsync(reg->peer[p] + (size_t)c->rank * slice, src, slice, cudaMemcpyDeviceToDevice, c->stream));
+            }
+            // barrier 2: every rank's copies (stream-ordered before its contribution) have landed
+            NC(g_nccl.AllReduce(c->d_bar, c->d_bar + 1, 1, ncclInt, ncclMax, c->comm, c->stream));
+        } else if (slice > 0) {
             NC(g_nccl.AllGather((const char*)gather_records + (size_t)c->rank * slice, gather_records, slice, ncclChar, c->comm, c->stream));
+        }
         CU(cudaEventRecord(c->gathered[slot], c->stream));
     } else {
         CU(cudaEventRecord(c->gathered[slot], st));

@@ -56,6 +56,14 @@ class Communicator:
         self.capi.check(self.lib.cpi_preintegrate_batch_sharded(self.handle, model, dtype, n_local, P(offsets), 0 if ns is None else ns, P(samples), P(lin),
                                                                 ctypes.c_void_p(sig.ctypes.data), flags, P(gather), ctypes.c_void_p(st.cuda_stream)))
 
+    def register(self, gather):
+        """Collective, once per gather buffer (same order on every rank): lets step() exchange the records with copy-engine peer copies
+        over NVLink instead of an NCCL all-gather kernel (cpi_comm_register).  Returns whether that path is active."""
+        import ctypes
+        flag = ctypes.c_int(0)
+        self.capi.check(self.lib.cpi_comm_register(self.handle, ctypes.c_void_p(gather.data_ptr()), gather.numel() * gather.element_size(), ctypes.byref(flag)))
+        return bool(flag.value)
+
     def wait(self, stream=None):
         import ctypes
         import torch

@@ -243,7 +243,7 @@ int64_t cpi_cut_windows(int64_t n_imu, const double* t, const double* w, const d
 /*
  * Windows share nothing but the four sigmas (the reference constructs a fresh preintegrator per factor,
  * solvers/GraphSolver_IMU.cpp:43), so a batch shards contiguously: rank r preintegrates its n_local windows and the only
- * exchange is ONE in-place NCCL all-gather of the fixed-size records, after which every rank -- in particular rank 0, where
+ * exchange is ONE in-place all-gather of the fixed-size records (NCCL, or copy-engine peer copies for registered buffers), after which every rank -- in particular rank 0, where
  * the solver lives -- holds all world * n_local records in window order.  NCCL is bound at run time (dlopen libnccl.so.2).
  *
  *   cpi_comm_unique_id   rank 0: 128-byte NCCL id to hand to the other ranks (any out-of-band channel)
@@ -254,7 +254,13 @@ int64_t cpi_cut_windows(int64_t n_imu, const double* t, const double* w, const d
  *        stream behind an event.  Returns without synchronising: the next batch's kernel (into ANOTHER gather buffer)
  *        overlaps the collective.  Re-using a gather buffer orders the new kernel behind that buffer's previous all-gather.
  *        n_local must be the same on every rank (pad a short last shard with zero-step windows).
- *   cpi_comm_wait        makes `stream` wait for the most recently enqueued all-gather (call before consuming the records)
+ *   cpi_comm_register    collective, optional, once per gather buffer (same buffers in the same order on every rank): exports the buffer
+ *        with CUDA IPC and maps the peers' buffers, after which cpi_preintegrate_batch_sharded exchanges the records by COPY-ENGINE
+ *        copies of every rank's slice into the peers' buffers over NVLink (two one-element NCCL all-reduces as barriers) instead of an
+ *        ncclAllGather kernel: no SM is taken from the preintegration kernel that runs beside the exchange.  *peer_copies (may be NULL)
+ *        tells whether that path is active; it is not when any rank could not export / import (e.g. memory from a VMM / async pool) --
+ *        the buffer then simply keeps the NCCL path.  The buffer must stay allocated until cpi_comm_destroy.
+ *   cpi_comm_wait        makes `stream` wait for the most recently enqueued exchange (call before consuming the records)
  * The usual NCCL rule applies: collectives of ANOTHER communicator on the same devices (e.g. an MPI / torch.distributed NCCL group)
  * must not be in flight at the same time as this communicator's all-gathers -- synchronise the device between the two.
  */
@@ -265,6 +271,7 @@ int cpi_comm_create(const void* id, int rank, int world, cpi_comm** out);
 int cpi_comm_destroy(cpi_comm* comm);
 int cpi_comm_rank(const cpi_comm* comm);
 int cpi_comm_world(const cpi_comm* comm);
+int cpi_comm_register(cpi_comm* comm, void* gather_records, size_t bytes, int* peer_copies);
 int cpi_preintegrate_batch_sharded(cpi_comm* comm, int model, int dtype, int64_t n_local,
                                    const int64_t* sample_offsets, int64_t ns_uniform,
                                    const void* samples, const void* lin, const double* sigmas, int flags,

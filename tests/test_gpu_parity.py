@@ -574,3 +574,18 @@ def test_chain_lm_step_reduces_the_cost(cuda):
     c0, c1, c2 = float(c0), float(c1), float(c2)
     print("cost", c0, c1, c2, "|dx|", float(dx.norm()), float(dx2.norm()), float(dx3.norm()))
     assert np.isfinite(c0) and c1 < 1e-3 * c0 and c2 <= c1 * 1.0001 and torch.all(torch.isfinite(X3))
+
+
+def test_sharded_entry_point_on_two_gpus(cuda):
+    """cpi_preintegrate_batch_sharded on two ranks (one per GPU), both exchange paths, several steps over alternating gather buffers:
+    every rank's gather buffer equals what the ranks computed on their own (tools/shard_check.py under torchrun).  Skipped on one GPU."""
+    import json, os, subprocess, sys
+    if cuda.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29541",
+                        os.path.join(root, "tools", "shard_check.py")], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rep = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert rep["mismatching_steps_over_all_ranks"] == 0
+    print("peer-copy path active:", [c["peer_copies"] for c in rep["cases"] if c["registered"]])
