@@ -388,7 +388,7 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
         torch.cuda.synchronize()             # nothing of torch's own NCCL group in flight while the product communicator runs collectives
         pushed = [ctx.comm.register(g) for g in gathers]
         exchange = ("copy-engine peer copies of every rank's slice into CUDA-IPC mappings of the peers' gather buffers + two 1-element NCCL all-reduces as barriers"
-                    if all(pushed) else "ncclAllGather (buffers could not be exported with CUDA IPC)")
+                    if all(pushed) else "ncclAllGather (CPI_B200_GATHER=nccl, or the buffers could not be exported with CUDA IPC)")
 
     def step(i):
         dS, dL = batches[i % NB]
@@ -533,6 +533,12 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
         if ctx.numa:
             out["e2e"]["host_numa"] = f"pinned host buffers allocated on the NUMA node of the rank's GPU (rank 0: node {ctx.numa['node']}, {ctx.numa['cpus']} cpus)"
         del hS, hL, hO
+    if world > 1:
+        # CUDA IPC: every rank drops its mappings of the peers' gather buffers, the ranks meet, and only then are the buffers freed
+        torch.cuda.synchronize()
+        ctx.comm.unregister()
+        dist.barrier()
+        torch.cuda.synchronize()
     del batches, gathers
     torch.cuda.empty_cache()
 

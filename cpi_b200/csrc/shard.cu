@@ -87,8 +87,8 @@ struct IpcMsg {                       // what every rank tells the others about 
     int32_t pad;
 };
 static_assert(sizeof(IpcMsg) == 88, "IpcMsg layout");
-struct OpenedAlloc { int peer; cudaIpcMemHandle_t handle; void* base; };
-struct Registered { void* local = nullptr; size_t bytes = 0; bool push = false; char* peer[MAX_WORLD] = {nullptr}; };
+struct OpenedAlloc { int peer; cudaIpcMemHandle_t handle; void* base; int refs; };
+struct Registered { void* local = nullptr; size_t bytes = 0; bool push = false; char* peer[MAX_WORLD] = {nullptr}; void* peer_base[MAX_WORLD] = {nullptr}; };
 
 }  // namespace
 
@@ -215,8 +215,10 @@ int cpi_comm_register(cpi_comm* c, void* gather_records, size_t bytes, int* peer
             for (auto& o : c->opened) if (o.peer == p && !memcmp(&o.handle, &all[p].handle, sizeof(cudaIpcMemHandle_t))) base = o.base;
             if (!base) {
                 if (cudaIpcOpenMemHandle(&base, all[p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); imported = 0; break; }
-                c->opened.push_back(OpenedAlloc{p, all[p].handle, base});
+                c->opened.push_back(OpenedAlloc{p, all[p].handle, base, 0});
             }
+            for (auto& o : c->opened) if (o.base == base) o.refs++;
+            reg.peer_base[p] = base;
             reg.peer[p] = (char*)base + all[p].offset;
         }
     }
@@ -230,6 +232,24 @@ int cpi_comm_register(cpi_comm* c, void* gather_records, size_t bytes, int* peer
     reg.push = agreed == 1;
     c->regs.push_back(reg);
     if (peer_copies) *peer_copies = reg.push ? 1 : 0;
+    return CPI_OK;
+}
+
+int cpi_comm_unregister(cpi_comm* c, void* gather_records) {
+    if (!c) return cpi::capi_fail(CPI_EINVAL, "null pointer argument");
+    CU(cudaStreamSynchronize(c->stream));                             // no exchange of this communicator in flight
+    for (size_t i = 0; i < c->regs.size();) {
+        if (gather_records && c->regs[i].local != gather_records) { i++; continue; }
+        for (int p = 0; p < c->world; p++)
+            if (c->regs[i].peer_base[p])
+                for (auto& o : c->opened) if (o.base == c->regs[i].peer_base[p]) o.refs--;
+        for (int k = 0; k < cpi_comm::NBUF; k++) if (c->buf[k] == c->regs[i].local) c->buf[k] = nullptr;
+        c->regs.erase(c->regs.begin() + i);
+    }
+    for (size_t i = 0; i < c->opened.size();) {
+        if (c->opened[i].refs <= 0) { cudaIpcCloseMemHandle(c->opened[i].base); c->opened.erase(c->opened.begin() + i); }
+        else i++;
+    }
     return CPI_OK;
 }
 

@@ -64,6 +64,12 @@ class Communicator:
         self.capi.check(self.lib.cpi_comm_register(self.handle, ctypes.c_void_p(gather.data_ptr()), gather.numel() * gather.element_size(), ctypes.byref(flag)))
         return bool(flag.value)
 
+    def unregister(self, gather=None):
+        """Drop the registration of one gather buffer (None: all).  Every rank must do this -- and the ranks must synchronise -- before
+        any rank frees the buffer."""
+        import ctypes
+        self.capi.check(self.lib.cpi_comm_unregister(self.handle, ctypes.c_void_p(gather.data_ptr() if gather is not None else 0)))
+
     def wait(self, stream=None):
         import ctypes
         import torch

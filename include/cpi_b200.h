@@ -259,7 +259,10 @@ int64_t cpi_cut_windows(int64_t n_imu, const double* t, const double* w, const d
  *        copies of every rank's slice into the peers' buffers over NVLink (two one-element NCCL all-reduces as barriers) instead of an
  *        ncclAllGather kernel: no SM is taken from the preintegration kernel that runs beside the exchange.  *peer_copies (may be NULL)
  *        tells whether that path is active; it is not when any rank could not export / import (e.g. memory from a VMM / async pool) --
- *        the buffer then simply keeps the NCCL path.  The buffer must stay allocated until cpi_comm_destroy.
+ *        the buffer then simply keeps the NCCL path.
+ *   cpi_comm_unregister  drops the registration of one buffer (NULL: of all) and closes the peer mappings nothing refers to any more.
+ *        EVERY rank must have unregistered a buffer before ANY rank frees it (freeing memory a peer still has mapped is undefined in
+ *        CUDA IPC): unregister, synchronise the ranks, then free.
  *   cpi_comm_wait        makes `stream` wait for the most recently enqueued exchange (call before consuming the records)
  * The usual NCCL rule applies: collectives of ANOTHER communicator on the same devices (e.g. an MPI / torch.distributed NCCL group)
  * must not be in flight at the same time as this communicator's all-gathers -- synchronise the device between the two.
@@ -272,6 +275,7 @@ int cpi_comm_destroy(cpi_comm* comm);
 int cpi_comm_rank(const cpi_comm* comm);
 int cpi_comm_world(const cpi_comm* comm);
 int cpi_comm_register(cpi_comm* comm, void* gather_records, size_t bytes, int* peer_copies);
+int cpi_comm_unregister(cpi_comm* comm, void* gather_records);
 int cpi_preintegrate_batch_sharded(cpi_comm* comm, int model, int dtype, int64_t n_local,
                                    const int64_t* sample_offsets, int64_t ns_uniform,
                                    const void* samples, const void* lin, const double* sigmas, int flags,

@@ -40,6 +40,10 @@ for model, dtype, n, ns in ((1, torch.float64, 1503, 60), (2, torch.float64, 700
             if not torch.equal(got, ref):
                 bad += 1
                 worst = max(worst, float((got.double() - ref.double()).abs().max()))
+        torch.cuda.synchronize()
+        comm.unregister()
+        dist.barrier()
+        torch.cuda.synchronize()
         report["cases"].append({"model": model, "dtype": str(dtype), "windows_per_rank": n, "registered": registered, "peer_copies": mode, "steps": 5,
                                 "max_abs_diff_vs_own_results": worst})
 t = torch.tensor([bad], device="cuda")
