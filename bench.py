@@ -380,8 +380,11 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
             dS = dS.repeat(reps, 1, 1)[:n].contiguous(); dL = dL.repeat(reps, 1)[:n].contiguous()
         batches.append((dS, dL))
     del S, L      # NB: dropping a 112 MB numpy array is a ~12 ms munmap on the host -- must not happen inside the timed loop
-    # rank r's kernel writes gathers[k][r] in place; two buffers so that step i's all-gather overlaps step i+1's kernel
-    gathers = [torch.empty((world, n, rd), dtype=tdt, device=dev) for _ in range(2 if world > 1 else 1)]
+    # rank r's kernel writes gathers[k][r] in place.  THREE buffers in rotation: step i's exchange overlaps step i+1's kernel, and its closing
+    # barrier -- an NCCL kernel, which gets SM resources only when the one-wave kernel beside it drains -- completes under step i+2's
+    # kernel instead of in front of it (with two buffers every step waited ~one all-reduce latency: 15 us at N = 2, ~90 us at N = 8)
+    NG = 3 if world > 1 else 1
+    gathers = [torch.empty((world, n, rd), dtype=tdt, device=dev) for _ in range(NG)]
     stream = torch.cuda.current_stream()
     exchange = None
     if world > 1:
@@ -393,7 +396,7 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
     def step(i):
         dS, dL = batches[i % NB]
         if world > 1:
-            ctx.comm.step(model, dS, dL, synth.SIGMAS, 0, gathers[i & 1], ns=ns, stream=stream)
+            ctx.comm.step(model, dS, dL, synth.SIGMAS, 0, gathers[i % NG], ns=ns, stream=stream)
         else:
             preint.preintegrate(model, dS, dL, synth.SIGMAS, 0, ns=ns, out=gathers[0][0], stream=stream)
 
