@@ -66,6 +66,10 @@ NCU_TRAFFIC = {   # dram__bytes_read.sum + dram__bytes_write.sum per launch of t
     "v1_125k_200": (1.4247e9 + 273.82e6, "profiles/r02_k1_tri_125k.txt"),                  # [1.703 GB]
     "v1_1m_200_fp32": (709.55e6 + 129.51e6, "profiles/r02_k1_tri_fp32_125k.txt"),          # [851.5 MB]
 }
+# sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed of the same captures: the hardware-utilisation figure next to the contract fraction
+# (model 2 executes ~55 % of the survey's 15 kflop/sample contract -- RK4 applied directly to the consumed Discrete_J_b columns -- so its
+# contract fraction overstates the pipe utilisation)
+NCU_FP64_PIPE_PCT = {"v1_10k_200": 43.8, "v2_100k_400": 49.7, "v1_125k_200": 50.6, "v1_1m_200_fp32": 21.6}
 
 
 def measured_peaks():
@@ -380,17 +384,17 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
             dS = dS.repeat(reps, 1, 1)[:n].contiguous(); dL = dL.repeat(reps, 1)[:n].contiguous()
         batches.append((dS, dL))
     del S, L      # NB: dropping a 112 MB numpy array is a ~12 ms munmap on the host -- must not happen inside the timed loop
-    # rank r's kernel writes gathers[k][r] in place.  THREE buffers in rotation: step i's exchange overlaps step i+1's kernel, and its closing
-    # barrier -- an NCCL kernel, which gets SM resources only when the one-wave kernel beside it drains -- completes under step i+2's
-    # kernel instead of in front of it (with two buffers every step waited ~one all-reduce latency: 15 us at N = 2, ~90 us at N = 8)
-    NG = 3 if world > 1 else 1
+    # rank r's kernel writes gathers[k][r] in place; two buffers in rotation, so that step i's exchange overlaps step i+1's kernel
+    NG = 2 if world > 1 else 1
     gathers = [torch.empty((world, n, rd), dtype=tdt, device=dev) for _ in range(NG)]
     stream = torch.cuda.current_stream()
     exchange = None
     if world > 1:
         torch.cuda.synchronize()             # nothing of torch's own NCCL group in flight while the product communicator runs collectives
         pushed = [ctx.comm.register(g) for g in gathers]
-        exchange = ("copy-engine peer copies of every rank's slice into CUDA-IPC mappings of the peers' gather buffers + two 1-element NCCL all-reduces as barriers"
+        smfree = ctx.comm.lib.cpi_comm_sm_free_barriers(ctx.comm.handle) == 1
+        exchange = ("copy-engine peer copies of every rank's slice into CUDA-IPC mappings of the peers' gather buffers, barriers = "
+                    + ("copy-engine flag writes + cuStreamWaitValue32 (no SM)" if smfree else "two 1-element NCCL all-reduces")
                     if all(pushed) else "ncclAllGather (CPI_B200_GATHER=nccl, or the buffers could not be exported with CUDA IPC)")
 
     def step(i):
@@ -468,6 +472,7 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
            "config": cfg, "gpu_launches": int(launches), "kernel_ms": kern_ms, **({"exchange": exchange} if exchange else {}),
            "roofline": {"bound": "fp32+fp64 CUDA cores" if f32 else "fp64", "achieved": ach_tf, "peak": FFMA_PEAK_TFLOPS if f32 else DFMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                         "frac": ach_tf / (FFMA_PEAK_TFLOPS if f32 else DFMA_PEAK_TFLOPS),
+                        "fp64_pipe_active_pct_ncu": NCU_FP64_PIPE_PCT.get(name),
                         "traffic": NCU_TRAFFIC.get(name, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(name, (None, None))[1],
                         "note": "CUDA-core FMA bound, not HBM/tensor (85 flop/B); peak = DFMA / FFMA microbenchmark measured on this pool (tools/microbench.cu, "
                                 "profiles/microbench_r02.jsonl); achieved = algorithmic flops (5.8 kflop/sample v1, 15 v2; SURVEY 8d) / CUDA-event kernel time "

@@ -40,6 +40,7 @@ SYMBOLS = {
     "cpi_comm_rank": (c_int, [c_vp]),
     "cpi_comm_world": (c_int, [c_vp]),
     "cpi_preintegrate_batch_sharded": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
+    "cpi_comm_sm_free_barriers": (c_int, [c_vp]),
     "cpi_comm_register": (c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "cpi_comm_unregister": (c_int, [c_vp, c_vp]),
     "cpi_comm_wait": (c_int, [c_vp, c_vp]),

@@ -54,6 +54,9 @@ std::mutex g_nccl_mu;
 // cuMemGetAddressRange_v2(CUdeviceptr* base, size_t* size, CUdeviceptr ptr): the allocation a pointer lives in (for the IPC handle)
 typedef int (*cuMemGetAddressRange_t)(unsigned long long*, size_t*, unsigned long long);
 cuMemGetAddressRange_t g_addr_range = nullptr;
+// cuStreamWriteValue32_v2 / cuStreamWaitValue32_v2(CUstream, CUdeviceptr, cuuint32_t value, unsigned flags): stream-ordered flag write / wait, no SM
+typedef int (*cuStreamOp32_t)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+cuStreamOp32_t g_write32 = nullptr, g_wait32 = nullptr;
 
 int nccl_load() {
     std::lock_guard<std::mutex> lk(g_nccl_mu);
@@ -71,6 +74,8 @@ int nccl_load() {
     if (void* cu = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL)) {
         *(void**)(&g_addr_range) = dlsym(cu, "cuMemGetAddressRange_v2");
         if (!g_addr_range) *(void**)(&g_addr_range) = dlsym(cu, "cuMemGetAddressRange");
+        *(void**)(&g_write32) = dlsym(cu, "cuStreamWriteValue32_v2");
+        *(void**)(&g_wait32) = dlsym(cu, "cuStreamWaitValue32_v2");
     }
     g_nccl = a;
     return CPI_OK;
@@ -107,9 +112,40 @@ struct cpi_comm {
     cudaEvent_t gathered[NBUF] = {nullptr};   // ... and the event recorded behind their last exchange
     int last = -1;
     int* d_bar = nullptr;                     // two ints: source / sink of the barrier all-reduces
+    // SM-free barriers: flags[kind][rank] of every rank, written by the peers with 4-byte copy-engine copies and awaited with stream
+    // wait-value operations.  An NCCL barrier kernel would have to find SM resources next to a kernel that fills the machine in one wave:
+    // it starts only when that kernel drains, and the next kernel on the same gather buffer waits for it (~90 us per step at N = 8).
+    uint32_t* flags = nullptr;                // [2][MAX_WORLD] flags + [2] staging words
+    uint32_t* peer_flags[64] = {nullptr};     // the peers' flag arrays (CUDA IPC)
+    void* peer_flags_base[64] = {nullptr};
+    uint32_t seq[2] = {0, 0};
+    bool ce_barrier = false;
     std::vector<Registered> regs;             // cpi_comm_register
     std::vector<OpenedAlloc> opened;          // peer allocations mapped with cudaIpcOpenMemHandle (one mapping per allocation)
 };
+
+namespace {
+// barrier over all ranks on stream s: returns when EVERY rank's stream s has reached its matching call
+int comm_barrier(cpi_comm* c, int kind, cudaStream_t s) {
+    if (!c->ce_barrier) {
+        NC(g_nccl.AllReduce(c->d_bar, c->d_bar + 1, 1, ncclInt, ncclMax, c->comm, s));
+        return CPI_OK;
+    }
+    const uint32_t v = ++c->seq[kind];
+    uint32_t* stage = c->flags + 2 * MAX_WORLD + kind;
+    if (g_write32(s, (unsigned long long)(uintptr_t)stage, v, 0) != 0) return cpi::capi_fail(CPI_ECUDA, "cuStreamWriteValue32 failed");
+    for (int k = 1; k < c->world; k++) {
+        const int p = (c->rank + k) % c->world;
+        CU(cudaMemcpyAsync(c->peer_flags[p] + kind * MAX_WORLD + c->rank, stage, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    }
+    for (int k = 1; k < c->world; k++) {
+        const int p = (c->rank + k) % c->world;
+        if (g_wait32(s, (unsigned long long)(uintptr_t)(c->flags + kind * MAX_WORLD + p), v, 0 /* CU_STREAM_WAIT_VALUE_GEQ */) != 0)
+            return cpi::capi_fail(CPI_ECUDA, "cuStreamWaitValue32 failed");
+    }
+    return CPI_OK;
+}
+}  // namespace
 
 extern "C" {
 
@@ -158,6 +194,49 @@ int cpi_comm_create(const void* id_in, int rank, int world, cpi_comm** out) {
     for (int i = 0; i < cpi_comm::NBUF; i++) CU(cudaEventCreateWithFlags(&c->gathered[i], cudaEventDisableTiming));
     CU(cudaMalloc(&c->d_bar, 2 * sizeof(int)));
     CU(cudaMemset(c->d_bar, 0, 2 * sizeof(int)));
+    // SM-free barriers (optional: falls back to one-element NCCL all-reduces when anything below is unavailable on ANY rank)
+    if (world > 1) {
+        const size_t fbytes = (2 * MAX_WORLD + 2) * sizeof(uint32_t);
+        CU(cudaMalloc(&c->flags, fbytes));
+        CU(cudaMemset(c->flags, 0, fbytes));
+        IpcMsg mine;
+        memset(&mine, 0, sizeof mine);
+        static const bool nccl_barrier = getenv("CPI_B200_BARRIER") && !strcmp(getenv("CPI_B200_BARRIER"), "nccl");
+        if (g_write32 && g_wait32 && !nccl_barrier && cudaIpcGetMemHandle(&mine.handle, c->flags) == cudaSuccess) {
+            // self-test of the stream memory operations on this device
+            uint32_t* stage = c->flags + 2 * MAX_WORLD;
+            if (g_write32(c->stream, (unsigned long long)(uintptr_t)stage, 7u, 0) == 0 &&
+                g_wait32(c->stream, (unsigned long long)(uintptr_t)stage, 7u, 0) == 0 && cudaStreamSynchronize(c->stream) == cudaSuccess) mine.ok = 1;
+            CU(cudaMemsetAsync(stage, 0, 2 * sizeof(uint32_t), c->stream));
+        }
+        cudaGetLastError();
+        std::vector<IpcMsg> all(world);
+        void* d_x = nullptr;
+        CU(cudaMalloc(&d_x, sizeof(IpcMsg) * world));
+        CU(cudaMemcpyAsync((char*)d_x + sizeof(IpcMsg) * rank, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+        NC(g_nccl.AllGather((char*)d_x + sizeof(IpcMsg) * rank, d_x, sizeof(IpcMsg), ncclChar, c->comm, c->stream));
+        CU(cudaMemcpyAsync(all.data(), d_x, sizeof(IpcMsg) * world, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFree(d_x));
+        int ok = 1;
+        for (int p = 0; p < world; p++) ok = ok && all[p].ok == 1;
+        if (ok) {
+            for (int p = 0; p < world && ok; p++) {
+                if (p == rank) { c->peer_flags[p] = c->flags; continue; }
+                void* base = nullptr;
+                if (cudaIpcOpenMemHandle(&base, all[p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+                c->peer_flags_base[p] = base;
+                c->peer_flags[p] = (uint32_t*)base;
+            }
+        }
+        int agreed = 0;
+        CU(cudaMemcpyAsync(c->d_bar, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        NC(g_nccl.AllReduce(c->d_bar, c->d_bar + 1, 1, ncclInt, ncclMin, c->comm, c->stream));
+        CU(cudaMemcpyAsync(&agreed, c->d_bar + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemsetAsync(c->d_bar, 0, 2 * sizeof(int), c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->ce_barrier = agreed == 1;
+    }
     *out = c;
     return CPI_OK;
 }
@@ -177,12 +256,15 @@ int cpi_comm_destroy(cpi_comm* c) {
     if (c->kernel_done) cudaEventDestroy(c->kernel_done);
     for (int i = 0; i < cpi_comm::NBUF; i++) if (c->gathered[i]) cudaEventDestroy(c->gathered[i]);
     if (c->d_bar) cudaFree(c->d_bar);
+    for (int p = 0; p < MAX_WORLD; p++) if (c->peer_flags_base[p]) cudaIpcCloseMemHandle(c->peer_flags_base[p]);
+    if (c->flags) cudaFree(c->flags);
     delete c;
     return CPI_OK;
 }
 
 int cpi_comm_rank(const cpi_comm* c) { return c ? c->rank : CPI_EINVAL; }
 int cpi_comm_world(const cpi_comm* c) { return c ? c->world : CPI_EINVAL; }
+int cpi_comm_sm_free_barriers(const cpi_comm* c) { return c ? (c->ce_barrier ? 1 : 0) : CPI_EINVAL; }
 
 int cpi_comm_register(cpi_comm* c, void* gather_records, size_t bytes, int* peer_copies) {
     if (peer_copies) *peer_copies = 0;
@@ -292,7 +374,7 @@ int cpi_preintegrate_batch_sharded(cpi_comm* c, int model, int dtype, int64_t n_
         // (whatever the caller enqueued before it -- e.g. the consumer of the buffer's previous contents -- is then done)
         CU(cudaEventRecord(c->entry, st));
         CU(cudaStreamWaitEvent(c->stream, c->entry, 0));
-        NC(g_nccl.AllReduce(c->d_bar, c->d_bar + 1, 1, ncclInt, ncclMax, c->comm, c->stream));
+        { const int brc = comm_barrier(c, 0, c->stream); if (brc) return brc; }
         CU(cudaEventRecord(c->released, c->stream));
     }
     int rc = cpi_preintegrate_batch(model, dtype, n_local, sample_offsets, ns_uniform, samples, lin, sigmas, flags,
@@ -316,7 +398,7 @@ int cpi_preintegrate_batch_sharded(cpi_comm* c, int model, int dtype, int64_t n_
                 CU(cudaStreamWaitEvent(c->stream, c->copied[j], 0));
             }
             // barrier 2: every rank's copies (ordered before its contribution) have landed
-            NC(g_nccl.AllReduce(c->d_bar, c->d_bar + 1, 1, ncclInt, ncclMax, c->comm, c->stream));
+            { const int brc = comm_barrier(c, 1, c->stream); if (brc) return brc; }
         } else if (slice > 0) {
             CU(cudaStreamWaitEvent(c->stream, c->kernel_done, 0));
             NC(g_nccl.AllGather((const char*)gather_records + (size_t)c->rank * slice, gather_records, slice, ncclChar, c->comm, c->stream));

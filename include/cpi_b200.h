@@ -256,8 +256,10 @@ int64_t cpi_cut_windows(int64_t n_imu, const double* t, const double* w, const d
  *        n_local must be the same on every rank (pad a short last shard with zero-step windows).
  *   cpi_comm_register    collective, optional, once per gather buffer (same buffers in the same order on every rank): exports the buffer
  *        with CUDA IPC and maps the peers' buffers, after which cpi_preintegrate_batch_sharded exchanges the records by COPY-ENGINE
- *        copies of every rank's slice into the peers' buffers over NVLink (two one-element NCCL all-reduces as barriers) instead of an
- *        ncclAllGather kernel: no SM is taken from the preintegration kernel that runs beside the exchange.  *peer_copies (may be NULL)
+ *        copies of every rank's slice into the peers' buffers over NVLink instead of an ncclAllGather kernel, bracketed by two barriers
+ *        that are SM-free as well (4-byte copy-engine writes into the peers' flag words + cuStreamWaitValue32; one-element NCCL
+ *        all-reduces where stream memory operations are unavailable): nothing is taken from, or has to wait for, the preintegration
+ *        kernel that runs beside the exchange.  *peer_copies (may be NULL)
  *        tells whether that path is active; it is not when any rank could not export / import (e.g. memory from a VMM / async pool) --
  *        the buffer then simply keeps the NCCL path.
  *   cpi_comm_unregister  drops the registration of one buffer (NULL: of all) and closes the peer mappings nothing refers to any more.
@@ -274,6 +276,7 @@ int cpi_comm_create(const void* id, int rank, int world, cpi_comm** out);
 int cpi_comm_destroy(cpi_comm* comm);
 int cpi_comm_rank(const cpi_comm* comm);
 int cpi_comm_world(const cpi_comm* comm);
+int cpi_comm_sm_free_barriers(const cpi_comm* comm);   /* 1: the peer-copy exchange synchronises with copy-engine flag writes + stream wait-value ops; 0: with NCCL all-reduces */
 int cpi_comm_register(cpi_comm* comm, void* gather_records, size_t bytes, int* peer_copies);
 int cpi_comm_unregister(cpi_comm* comm, void* gather_records);
 int cpi_preintegrate_batch_sharded(cpi_comm* comm, int model, int dtype, int64_t n_local,
