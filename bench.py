@@ -473,6 +473,9 @@ def measure_preint(ctx, name, args, steps, warmup, distinct=None, e2e=True, cpu=
            "roofline": {"bound": "fp32+fp64 CUDA cores" if f32 else "fp64", "achieved": ach_tf, "peak": FFMA_PEAK_TFLOPS if f32 else DFMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                         "frac": ach_tf / (FFMA_PEAK_TFLOPS if f32 else DFMA_PEAK_TFLOPS),
                         "fp64_pipe_active_pct_ncu": NCU_FP64_PIPE_PCT.get(name),
+                        **({"contract_vs_executed": "model 2 executes ~8 k fp64 flop-equivalents per window-sample (ncu pipe counters; RK4 applied directly to the consumed "
+                                                    "Discrete_J_b columns, Phi never formed) against the survey's 15 k contract, so this contract fraction can exceed 1 and says "
+                                                    "nothing about the pipe: fp64_pipe_active_pct_ncu is the utilisation figure"} if model == 2 else {}),
                         "traffic": NCU_TRAFFIC.get(name, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(name, (None, None))[1],
                         "note": "CUDA-core FMA bound, not HBM/tensor (85 flop/B); peak = DFMA / FFMA microbenchmark measured on this pool (tools/microbench.cu, "
                                 "profiles/microbench_r02.jsonl); achieved = algorithmic flops (5.8 kflop/sample v1, 15 v2; SURVEY 8d) / CUDA-event kernel time "
