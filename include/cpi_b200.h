@@ -124,10 +124,11 @@ int cpi_preintegrate_batch_continue(int model, int dtype, int64_t n_windows,
                                     void* records, void* stream);
 
 /* Same with HOST buffers: H2D + kernel + D2H, synchronous, through device buffers owned by the library; batches above 16 MB are
- * pipelined: in up to 16 whole-window chunks (copy-in of chunk k+1 under the kernel of chunk k, copy-out under the next kernel), or
- * -- uniform layout, fp64, default modes -- as a WAVEFRONT of (window group x sample segment) tiles: strided tile copies along
- * anti-diagonals, each followed by a continuation kernel, so that every window's sample chain runs while its samples arrive and only
- * one segment of one group is left behind the last byte (results agree with the device entry point to rounding, ~1e-15).  sample_offsets
+ * pipelined in up to 16 whole-window chunks (copy-in of chunk k+1 under the kernel of chunk k, copy-out under the next kernel); with a
+ * uniform layout in the default fp64 modes the LAST windows of the batch (as many as take about one sample chain to transfer) travel
+ * sample-major instead -- four strided segment copies, each followed by a continuation kernel over those windows -- so that their
+ * chains of dependent samples run while the samples are still arriving and only a quarter of one chain is left behind the last byte
+ * (results agree with the device entry point to rounding, ~1e-15; CPI_B200_HOST_WAVE="groups,segments[,head %]" overrides).  sample_offsets
  * is a HOST array.  The copies are cudaMemcpyAsync straight from / to the caller's buffers: PINNED buffers (cudaHostAlloc, or
  * cpi_host_register below) overlap with the kernels; pageable buffers are legal but the CUDA driver stages them synchronously, so
  * the pipeline degrades to copy-then-compute.  Calls from several host threads serialise on the library's scratch buffers. */
